@@ -1,0 +1,643 @@
+// C ABI (include/fluid_b200.h): context, argument validation, operator
+// orchestration.  No arithmetic of the sim lives here — only which kernels run
+// in which order on which buffers.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "kernels.h"
+
+using namespace fs;
+
+enum Scratch { S_VTMP = 0, S_CTMP, S_DIV, S_P, S_P2, S_HV, S_HV2, S_HC, S_HC2, S_HP, S_HD, S_HIMG, S_COUNT };
+
+struct fs_ctx {
+    int device;
+    cudaStream_t stream;
+    int num_sms;
+    uint64_t launches;
+    void *scratch[S_COUNT];
+    size_t scratch_bytes[S_COUNT];
+    int *status_dev;            // device flag raised by tile advects (FS_ERR_HALO_OVERRUN)
+    unsigned int *maxdisp_dev;  // max-displacement reduction cell
+    int opt_sor, opt_sor_t, opt_advect, opt_fuse;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev;
+    bool changed;
+    explicit DeviceGuard(int dev) : prev(-1), changed(false)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+            cudaSetDevice(dev);
+            changed = true;
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+
+int ensure(fs_ctx *ctx, Scratch slot, size_t bytes, void **out)
+{
+    if (ctx->scratch_bytes[slot] < bytes) {
+        if (ctx->scratch[slot]) {
+            // the old buffer may still be in use by enqueued work
+            FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            FS_CUDA_TRY(cudaFree(ctx->scratch[slot]));
+            ctx->scratch[slot] = nullptr;
+            ctx->scratch_bytes[slot] = 0;
+        }
+        FS_CUDA_TRY(cudaMalloc(&ctx->scratch[slot], bytes));
+        ctx->scratch_bytes[slot] = bytes;
+    }
+    *out = ctx->scratch[slot];
+    return FS_OK;
+}
+
+inline Launch mk(fs_ctx *ctx) { return Launch{ctx->stream, &ctx->launches, ctx->num_sms}; }
+
+inline bool bad_dims(int dim_x, int dim_y)
+{
+    // the reference's domain_iter visits nodes twice when a dimension is 1
+    // (operations.h:26-37); 2 is the smallest well-defined grid.  Indices are
+    // 32-bit in the reference (operations.h:7-9).
+    return dim_x < 2 || dim_y < 2 || (long long)dim_x * dim_y > 0x7fffffffLL;
+}
+
+bool bad_tile(const fs_tile *t, int need_ring)
+{
+    if (!t) return true;
+    if (bad_dims(t->gdim_x, t->gdim_y) || t->nx < 1 || t->ny < 1) return true;
+    if (t->x0 < 0 || t->y0 < 0 || t->x1 > t->nx || t->y1 > t->ny || t->x0 > t->x1 || t->y0 > t->y1)
+        return true;
+    // the window must lie inside the global grid
+    if (t->ox < 0 || t->oy < 0 || t->ox + t->nx > t->gdim_x || t->oy + t->ny > t->gdim_y) return true;
+    // every computed node needs `need_ring` neighbours inside the window unless
+    // the global wall cuts them off
+    if (need_ring > 0 && t->x1 > t->x0 && t->y1 > t->y0) {
+        if (t->x0 - need_ring < 0 && t->ox + t->x0 - need_ring >= 0) return true;
+        if (t->y0 - need_ring < 0 && t->oy + t->y0 - need_ring >= 0) return true;
+        if (t->x1 + need_ring > t->nx && t->ox + t->x1 + need_ring <= t->gdim_x) return true;
+        if (t->y1 + need_ring > t->ny && t->oy + t->y1 + need_ring <= t->gdim_y) return true;
+    }
+    return false;
+}
+
+// rectangle grown by r, clipped to the window (== clipped to the global grid
+// when bad_tile(t, r) passed)
+Geo grown(const Geo &g, int r)
+{
+    Geo o = g;
+    o.x0 = g.x0 - r < 0 ? 0 : g.x0 - r;
+    o.y0 = g.y0 - r < 0 ? 0 : g.y0 - r;
+    o.x1 = g.x1 + r > g.nx ? g.nx : g.x1 + r;
+    o.y1 = g.y1 + r > g.ny ? g.ny : g.y1 + r;
+    return o;
+}
+
+// ---- operator cores over a Geo ------------------------------------------------
+
+int core_advect_vec2f(fs_ctx *ctx, fs_vec2f *next_p, const fs_vec2f *p, const fs_vec2f *vel,
+                      const Geo &g, float dt, int no_slip, int *status)
+{
+    return launch_advect_vec2f_gather(mk(ctx), (float2 *)next_p, (const float2 *)p,
+                                      (const float2 *)vel, g, dt, no_slip != 0, status);
+}
+
+int core_advect_rgb(fs_ctx *ctx, fs_rgb_uq32 *next_c, const fs_rgb_uq32 *c, const fs_vec2f *vel,
+                    const Geo &g, float dt, int no_slip, int *status)
+{
+    return launch_advect_rgb_gather(mk(ctx), (uint32_t *)next_c, (const uint32_t *)c,
+                                    (const float2 *)vel, g, dt, no_slip != 0, status);
+}
+
+// poisson_solve over a whole grid: zero, then iters x (colour 0, colour 1)
+int core_poisson_solve(fs_ctx *ctx, float *p, const float *div, const Geo &g, float dx, int iters,
+                       float omega)
+{
+    FS_CUDA_TRY(cudaMemsetAsync(p, 0, sizeof(float) * (size_t)g.nx * g.ny, ctx->stream));
+    for (int k = 0; k < iters; k++) {
+        int e = launch_sor_half_sweep(mk(ctx), p, div, g, dx, omega, 0);
+        if (e) return e;
+        e = launch_sor_half_sweep(mk(ctx), p, div, g, dx, omega, 1);
+        if (e) return e;
+    }
+    return FS_OK;
+}
+
+// loop() body, ino:249-289.  v is advected into v_tmp, forced and projected
+// there, and the projection's last operator writes back into v (out of place
+// gradient-subtract), so the reference's pointer swap (ino:255) costs no copy.
+// The dye goes c_in -> c_out.
+int core_step(fs_ctx *ctx, fs_vec2f *v, fs_vec2f *v_tmp, const fs_rgb_uq32 *c_in,
+              fs_rgb_uq32 *c_out, const fs_drag *drags, int n_drags, int dim_x, int dim_y, float dt,
+              float dx, int iters, float omega, float *p, float *div)
+{
+    const Geo g = geo_full(dim_x, dim_y);
+    int e;
+    if ((e = core_advect_vec2f(ctx, v_tmp, v, v, g, dt, 1, nullptr))) return e;           // ino:253
+    if (n_drags > 0 && (e = launch_apply_drags(mk(ctx), (float2 *)v_tmp, drags, n_drags, g)))
+        return e;                                                                        // ino:264-269
+    if ((e = launch_divergence(mk(ctx), div, (const float2 *)v_tmp, g, dx))) return e;    // ino:274
+    if ((e = core_poisson_solve(ctx, p, div, g, dx, iters, omega))) return e;             // ino:275
+    if ((e = launch_subtract_gradient(mk(ctx), (float2 *)v, (const float2 *)v_tmp, p, g, dx)))
+        return e;                                                                        // ino:276
+    if ((e = core_advect_rgb(ctx, c_out, c_in, v, g, dt, 0, nullptr))) return e;          // ino:282
+    return FS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *fs_version(void) { return "fluid_b200 0.1 (sm_100a)"; }
+
+const char *fs_error_string(int code)
+{
+    switch (code) {
+        case FS_OK: return "ok";
+        case FS_ERR_INVALID_ARG: return "invalid argument";
+        case FS_ERR_NO_CONTEXT: return "no context";
+        case FS_ERR_UNSUPPORTED: return "unsupported";
+        case FS_ERR_HALO_OVERRUN: return "advect backtrace left the local window";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int fs_ctx_create(fs_ctx **out, int device, void *stream)
+{
+    if (!out) return FS_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    FS_CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return (int)cudaErrorInvalidDevice;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    FS_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return (int)cudaErrorNoKernelImageForDevice;  // sm_100a only, no fallback
+    fs_ctx *ctx = new (std::nothrow) fs_ctx();
+    if (!ctx) return (int)cudaErrorMemoryAllocation;
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    ctx->stream = (cudaStream_t)stream;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->opt_sor = 1;
+    ctx->opt_sor_t = 4;
+    ctx->opt_advect = 1;
+    ctx->opt_fuse = 1;
+    cudaError_t e = cudaMalloc(&ctx->status_dev, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->maxdisp_dev, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(ctx->status_dev, 0, sizeof(int));
+    if (e != cudaSuccess) {
+        delete ctx;
+        return (int)e;
+    }
+    *out = ctx;
+    return FS_OK;
+}
+
+int fs_ctx_destroy(fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int s = 0; s < S_COUNT; s++)
+        if (ctx->scratch[s]) cudaFree(ctx->scratch[s]);
+    cudaFree(ctx->status_dev);
+    cudaFree(ctx->maxdisp_dev);
+    delete ctx;
+    return FS_OK;
+}
+
+int fs_ctx_synchronize(fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    DeviceGuard guard(ctx->device);
+    FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return FS_OK;
+}
+
+static int *opt_slot(fs_ctx *ctx, const char *name)
+{
+    if (!strcmp(name, "sor")) return &ctx->opt_sor;
+    if (!strcmp(name, "sor_t")) return &ctx->opt_sor_t;
+    if (!strcmp(name, "advect")) return &ctx->opt_advect;
+    if (!strcmp(name, "fuse")) return &ctx->opt_fuse;
+    return nullptr;
+}
+
+int fs_ctx_set_option(fs_ctx *ctx, const char *name, int value)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!name) return FS_ERR_INVALID_ARG;
+    int *slot = opt_slot(ctx, name);
+    if (!slot) return FS_ERR_INVALID_ARG;
+    if (slot == &ctx->opt_sor_t && (value < 1 || value > 8)) return FS_ERR_INVALID_ARG;
+    *slot = value;
+    return FS_OK;
+}
+
+int fs_ctx_get_option(fs_ctx *ctx, const char *name, int *value)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!name || !value) return FS_ERR_INVALID_ARG;
+    int *slot = opt_slot(ctx, name);
+    if (!slot) return FS_ERR_INVALID_ARG;
+    *value = *slot;
+    return FS_OK;
+}
+
+uint64_t fs_ctx_launch_count(fs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int fs_host_alloc(void **out, size_t bytes)
+{
+    if (!out) return FS_ERR_INVALID_ARG;
+    FS_CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return FS_OK;
+}
+
+int fs_host_free(void *p)
+{
+    FS_CUDA_TRY(cudaFreeHost(p));
+    return FS_OK;
+}
+
+// ---- device-pointer operators ---------------------------------------------------
+
+int fs_advect_vec2f(fs_vec2f *next_p, const fs_vec2f *p, const fs_vec2f *vel, int dim_x, int dim_y,
+                    float dt, int no_slip, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!next_p || !p || !vel || bad_dims(dim_x, dim_y) || next_p == p || next_p == vel)
+        return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return core_advect_vec2f(ctx, next_p, p, vel, geo_full(dim_x, dim_y), dt, no_slip, nullptr);
+}
+
+int fs_advect_rgb_uq32(fs_rgb_uq32 *next_c, const fs_rgb_uq32 *c, const fs_vec2f *vel, int dim_x,
+                       int dim_y, float dt, int no_slip, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!next_c || !c || !vel || bad_dims(dim_x, dim_y) || next_c == c) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return core_advect_rgb(ctx, next_c, c, vel, geo_full(dim_x, dim_y), dt, no_slip, nullptr);
+}
+
+int fs_calculate_divergence(float *div, const fs_vec2f *v, int dim_x, int dim_y, float dx,
+                            fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!div || !v || bad_dims(dim_x, dim_y)) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return launch_divergence(mk(ctx), div, (const float2 *)v, geo_full(dim_x, dim_y), dx);
+}
+
+int fs_subtract_gradient(fs_vec2f *v, const float *p, int dim_x, int dim_y, float dx, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!v || !p || bad_dims(dim_x, dim_y)) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return launch_subtract_gradient(mk(ctx), (float2 *)v, (const float2 *)v, p,
+                                    geo_full(dim_x, dim_y), dx);
+}
+
+int fs_poisson_solve(float *p, const float *div, int dim_x, int dim_y, float dx, int iters,
+                     float omega, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!p || !div || p == div || bad_dims(dim_x, dim_y) || iters < 0) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return core_poisson_solve(ctx, p, div, geo_full(dim_x, dim_y), dx, iters, omega);
+}
+
+int fs_sor_half_sweep(float *p, const float *div, int dim_x, int dim_y, float dx, float omega,
+                      int parity, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!p || !div || p == div || bad_dims(dim_x, dim_y)) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return launch_sor_half_sweep(mk(ctx), p, div, geo_full(dim_x, dim_y), dx, omega, parity);
+}
+
+int fs_apply_drags(fs_vec2f *v, const fs_drag *drags, int n, int dim_x, int dim_y, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!v || n < 0 || (n > 0 && !drags) || bad_dims(dim_x, dim_y)) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return launch_apply_drags(mk(ctx), (float2 *)v, drags, n, geo_full(dim_x, dim_y));
+}
+
+int fs_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags, int n_drags, int dim_x, int dim_y,
+            float dt, float dx, int iters, float omega, float *p_out, float *div_out, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!v || !c || n_drags < 0 || (n_drags > 0 && !drags) || bad_dims(dim_x, dim_y) || iters < 0)
+        return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    const size_t n = (size_t)dim_x * dim_y;
+    void *v_tmp, *c_tmp, *p = p_out, *d = div_out;
+    int e;
+    if ((e = ensure(ctx, S_VTMP, n * sizeof(fs_vec2f), &v_tmp))) return e;
+    if ((e = ensure(ctx, S_CTMP, n * sizeof(fs_rgb_uq32), &c_tmp))) return e;
+    if (!p && (e = ensure(ctx, S_P, n * sizeof(float), &p))) return e;
+    if (!d && (e = ensure(ctx, S_DIV, n * sizeof(float), &d))) return e;
+    if ((e = core_step(ctx, v, (fs_vec2f *)v_tmp, c, (fs_rgb_uq32 *)c_tmp, drags, n_drags, dim_x,
+                       dim_y, dt, dx, iters, omega, (float *)p, (float *)d)))
+        return e;
+    // the reference swaps pointers (ino:286); a raw-pointer ABI has to copy back
+    FS_CUDA_TRY(cudaMemcpyAsync(c, c_tmp, n * sizeof(fs_rgb_uq32), cudaMemcpyDeviceToDevice,
+                                ctx->stream));
+    return FS_OK;
+}
+
+int fs_upscale4_rgb565(uint16_t *out, const fs_rgb_uq32 *c, int dim_x, int dim_y, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!out || !c || bad_dims(dim_x, dim_y)) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return launch_upscale4_rgb565(mk(ctx), out, (const uint32_t *)c, dim_x, dim_y);
+}
+
+int fs_ensemble_step(fs_vec2f *, fs_rgb_uq32 *, const fs_drag *, const int *, int, int, int, int,
+                     float, float, int, float, int, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    return FS_ERR_UNSUPPORTED;
+}
+
+// ---- host-pointer drop-ins --------------------------------------------------------
+
+#define H2D(dst, src, bytes) FS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream))
+#define D2H(dst, src, bytes) FS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream))
+
+int fsh_advect_vec2f(fs_vec2f *next_p, const fs_vec2f *p, const fs_vec2f *vel, int dim_x, int dim_y,
+                     float dt, int no_slip, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!next_p || !p || !vel || bad_dims(dim_x, dim_y) || next_p == p || next_p == vel)
+        return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    const size_t bytes = (size_t)dim_x * dim_y * sizeof(fs_vec2f);
+    void *d_p, *d_vel, *d_out;
+    int e;
+    if ((e = ensure(ctx, S_HV, bytes, &d_p))) return e;
+    if ((e = ensure(ctx, S_VTMP, bytes, &d_out))) return e;
+    H2D(d_p, p, bytes);
+    d_vel = d_p;
+    if (vel != p) {
+        if ((e = ensure(ctx, S_HV2, bytes, &d_vel))) return e;
+        H2D(d_vel, vel, bytes);
+    }
+    if ((e = core_advect_vec2f(ctx, (fs_vec2f *)d_out, (fs_vec2f *)d_p, (fs_vec2f *)d_vel,
+                               geo_full(dim_x, dim_y), dt, no_slip, nullptr)))
+        return e;
+    D2H(next_p, d_out, bytes);
+    FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return FS_OK;
+}
+
+int fsh_advect_rgb_uq32(fs_rgb_uq32 *next_c, const fs_rgb_uq32 *c, const fs_vec2f *vel, int dim_x,
+                        int dim_y, float dt, int no_slip, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!next_c || !c || !vel || bad_dims(dim_x, dim_y) || next_c == c) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    const size_t n = (size_t)dim_x * dim_y;
+    void *d_c, *d_vel, *d_out;
+    int e;
+    if ((e = ensure(ctx, S_HC, n * sizeof(fs_rgb_uq32), &d_c))) return e;
+    if ((e = ensure(ctx, S_HV, n * sizeof(fs_vec2f), &d_vel))) return e;
+    if ((e = ensure(ctx, S_CTMP, n * sizeof(fs_rgb_uq32), &d_out))) return e;
+    H2D(d_c, c, n * sizeof(fs_rgb_uq32));
+    H2D(d_vel, vel, n * sizeof(fs_vec2f));
+    if ((e = core_advect_rgb(ctx, (fs_rgb_uq32 *)d_out, (fs_rgb_uq32 *)d_c, (fs_vec2f *)d_vel,
+                             geo_full(dim_x, dim_y), dt, no_slip, nullptr)))
+        return e;
+    D2H(next_c, d_out, n * sizeof(fs_rgb_uq32));
+    FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return FS_OK;
+}
+
+int fsh_calculate_divergence(float *div, const fs_vec2f *v, int dim_x, int dim_y, float dx,
+                             fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!div || !v || bad_dims(dim_x, dim_y)) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    const size_t n = (size_t)dim_x * dim_y;
+    void *d_v, *d_div;
+    int e;
+    if ((e = ensure(ctx, S_HV, n * sizeof(fs_vec2f), &d_v))) return e;
+    if ((e = ensure(ctx, S_HD, n * sizeof(float), &d_div))) return e;
+    H2D(d_v, v, n * sizeof(fs_vec2f));
+    if ((e = launch_divergence(mk(ctx), (float *)d_div, (const float2 *)d_v, geo_full(dim_x, dim_y), dx)))
+        return e;
+    D2H(div, d_div, n * sizeof(float));
+    FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return FS_OK;
+}
+
+int fsh_subtract_gradient(fs_vec2f *v, const float *p, int dim_x, int dim_y, float dx, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!v || !p || bad_dims(dim_x, dim_y)) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    const size_t n = (size_t)dim_x * dim_y;
+    void *d_v, *d_p;
+    int e;
+    if ((e = ensure(ctx, S_HV, n * sizeof(fs_vec2f), &d_v))) return e;
+    if ((e = ensure(ctx, S_HP, n * sizeof(float), &d_p))) return e;
+    H2D(d_v, v, n * sizeof(fs_vec2f));
+    H2D(d_p, p, n * sizeof(float));
+    if ((e = launch_subtract_gradient(mk(ctx), (float2 *)d_v, (const float2 *)d_v, (const float *)d_p,
+                                      geo_full(dim_x, dim_y), dx)))
+        return e;
+    D2H(v, d_v, n * sizeof(fs_vec2f));
+    FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return FS_OK;
+}
+
+int fsh_poisson_solve(float *p, const float *div, int dim_x, int dim_y, float dx, int iters,
+                      float omega, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!p || !div || p == div || bad_dims(dim_x, dim_y) || iters < 0) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    const size_t n = (size_t)dim_x * dim_y;
+    void *d_p, *d_div;
+    int e;
+    if ((e = ensure(ctx, S_HP, n * sizeof(float), &d_p))) return e;
+    if ((e = ensure(ctx, S_HD, n * sizeof(float), &d_div))) return e;
+    H2D(d_div, div, n * sizeof(float));
+    if ((e = core_poisson_solve(ctx, (float *)d_p, (const float *)d_div, geo_full(dim_x, dim_y), dx,
+                                iters, omega)))
+        return e;
+    D2H(p, d_p, n * sizeof(float));
+    FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return FS_OK;
+}
+
+int fsh_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags, int n_drags, int dim_x, int dim_y,
+             float dt, float dx, int iters, float omega, float *p_out, float *div_out, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!v || !c || n_drags < 0 || (n_drags > 0 && !drags) || bad_dims(dim_x, dim_y) || iters < 0)
+        return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    const size_t n = (size_t)dim_x * dim_y;
+    void *d_v, *d_vtmp, *d_c, *d_c2, *d_p, *d_div;
+    int e;
+    if ((e = ensure(ctx, S_HV, n * sizeof(fs_vec2f), &d_v))) return e;
+    if ((e = ensure(ctx, S_VTMP, n * sizeof(fs_vec2f), &d_vtmp))) return e;
+    if ((e = ensure(ctx, S_HC, n * sizeof(fs_rgb_uq32), &d_c))) return e;
+    if ((e = ensure(ctx, S_HC2, n * sizeof(fs_rgb_uq32), &d_c2))) return e;
+    if ((e = ensure(ctx, S_P, n * sizeof(float), &d_p))) return e;
+    if ((e = ensure(ctx, S_DIV, n * sizeof(float), &d_div))) return e;
+    H2D(d_v, v, n * sizeof(fs_vec2f));
+    H2D(d_c, c, n * sizeof(fs_rgb_uq32));
+    if ((e = core_step(ctx, (fs_vec2f *)d_v, (fs_vec2f *)d_vtmp, (fs_rgb_uq32 *)d_c,
+                       (fs_rgb_uq32 *)d_c2, drags, n_drags, dim_x, dim_y, dt, dx, iters, omega,
+                       (float *)d_p, (float *)d_div)))
+        return e;
+    D2H(v, d_v, n * sizeof(fs_vec2f));
+    D2H(c, d_c2, n * sizeof(fs_rgb_uq32));
+    if (p_out) D2H(p_out, d_p, n * sizeof(float));
+    if (div_out) D2H(div_out, d_div, n * sizeof(float));
+    FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return FS_OK;
+}
+
+int fsh_upscale4_rgb565(uint16_t *out, const fs_rgb_uq32 *c, int dim_x, int dim_y, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!out || !c || bad_dims(dim_x, dim_y)) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    const size_t n = (size_t)dim_x * dim_y;
+    const size_t img = 16 * (size_t)(dim_x - 1) * (dim_y - 1) * sizeof(uint16_t);
+    void *d_c, *d_img;
+    int e;
+    if ((e = ensure(ctx, S_HC, n * sizeof(fs_rgb_uq32), &d_c))) return e;
+    if ((e = ensure(ctx, S_HIMG, img ? img : 16, &d_img))) return e;
+    H2D(d_c, c, n * sizeof(fs_rgb_uq32));
+    if ((e = launch_upscale4_rgb565(mk(ctx), (uint16_t *)d_img, (const uint32_t *)d_c, dim_x, dim_y)))
+        return e;
+    if (img) D2H(out, d_img, img);
+    FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return FS_OK;
+}
+
+// ---- decomposed grids ---------------------------------------------------------------
+
+int fs_tile_advect_vec2f(fs_vec2f *next_p, const fs_vec2f *p, const fs_vec2f *vel, const fs_tile *t,
+                         float dt, int no_slip, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!next_p || !p || !vel || bad_tile(t, 0) || next_p == p || next_p == vel)
+        return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return core_advect_vec2f(ctx, next_p, p, vel, geo_tile(*t), dt, no_slip, ctx->status_dev);
+}
+
+int fs_tile_advect_rgb_uq32(fs_rgb_uq32 *next_c, const fs_rgb_uq32 *c, const fs_vec2f *vel,
+                            const fs_tile *t, float dt, int no_slip, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!next_c || !c || !vel || bad_tile(t, 0) || next_c == c) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return core_advect_rgb(ctx, next_c, c, vel, geo_tile(*t), dt, no_slip, ctx->status_dev);
+}
+
+int fs_tile_calculate_divergence(float *div, const fs_vec2f *v, const fs_tile *t, float dx,
+                                 fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!div || !v || bad_tile(t, 1)) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return launch_divergence(mk(ctx), div, (const float2 *)v, geo_tile(*t), dx);
+}
+
+int fs_tile_subtract_gradient(fs_vec2f *v, const float *p, const fs_tile *t, float dx, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!v || !p || bad_tile(t, 1)) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return launch_subtract_gradient(mk(ctx), (float2 *)v, (const float2 *)v, p, geo_tile(*t), dx);
+}
+
+int fs_tile_sor_sweeps(float *p_out, const float *p_in, const float *div, const fs_tile *t, float dx,
+                       float omega, int first_parity, int n_half, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!p_out || !div || p_out == p_in || p_out == div || n_half < 0 || bad_tile(t, n_half))
+        return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    const Geo g = geo_tile(*t);
+    // seed p_out on the rectangle grown by n_half, then sweep in place on
+    // rectangles that shrink by one node per half-sweep
+    const Geo seed = grown(g, n_half);
+    const size_t w = (size_t)(seed.x1 - seed.x0) * sizeof(float), h = seed.y1 - seed.y0;
+    if (w == 0 || h == 0) return FS_OK;
+    const size_t off = (size_t)seed.y0 * g.nx + seed.x0, pitch = (size_t)g.nx * sizeof(float);
+    if (p_in) {
+        FS_CUDA_TRY(cudaMemcpy2DAsync(p_out + off, pitch, p_in + off, pitch, w, h,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        FS_CUDA_TRY(cudaMemset2DAsync(p_out + off, pitch, 0, w, h, ctx->stream));
+    }
+    for (int s = 0; s < n_half; s++) {
+        int e = launch_sor_half_sweep(mk(ctx), p_out, div, grown(g, n_half - 1 - s), dx, omega,
+                                      (first_parity + s) & 1);
+        if (e) return e;
+    }
+    return FS_OK;
+}
+
+int fs_tile_apply_drags(fs_vec2f *v, const fs_drag *drags, int n, const fs_tile *t, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!v || n < 0 || (n > 0 && !drags) || bad_tile(t, 0)) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return launch_apply_drags(mk(ctx), (float2 *)v, drags, n, geo_tile(*t));
+}
+
+int fs_tile_check(fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    DeviceGuard guard(ctx->device);
+    int flag = 0;
+    FS_CUDA_TRY(cudaMemcpyAsync(&flag, ctx->status_dev, sizeof(int), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+    FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (flag) {
+        FS_CUDA_TRY(cudaMemsetAsync(ctx->status_dev, 0, sizeof(int), ctx->stream));
+        return flag;
+    }
+    return FS_OK;
+}
+
+int fs_tile_max_displacement(int *out_nodes, const fs_vec2f *vel, const fs_tile *t, float dt,
+                             fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!out_nodes || !vel || bad_tile(t, 0)) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    int e = launch_max_displacement(mk(ctx), ctx->maxdisp_dev, (const float2 *)vel, geo_tile(*t));
+    if (e) return e;
+    unsigned int bits = 0;
+    FS_CUDA_TRY(cudaMemcpyAsync(&bits, ctx->maxdisp_dev, sizeof(bits), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+    FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    float m;
+    memcpy(&m, &bits, sizeof(m));
+    // |v*dt| <= m*|dt| up to one rounding; +1 node covers it and the +1 corner of the bilinear cell
+    double d = (double)m * (dt < 0 ? -(double)dt : (double)dt);
+    long long nodes = (long long)d + 2;
+    *out_nodes = nodes > 0x3fffffff ? 0x3fffffff : (int)nodes;
+    return FS_OK;
+}
+
+}  // extern "C"

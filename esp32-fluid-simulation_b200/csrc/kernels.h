@@ -1,0 +1,37 @@
+// Host-side launchers of the sm_100a kernels (one per operator variant).  All
+// take a Geo (fs_common.cuh) so the same kernels serve a whole grid on one GPU
+// and a rank's padded window of a decomposed grid.  Each returns a cudaError_t
+// cast to int (0 = ok) and bumps *launches by the number of kernels enqueued.
+#pragma once
+
+#include "fs_common.cuh"
+
+namespace fs {
+
+struct Launch {
+    cudaStream_t stream;
+    uint64_t *launches;  // counter owned by the context
+    int num_sms;
+};
+
+// advect.cu — advect.h:74-85
+int launch_advect_vec2f_gather(const Launch &L, float2 *next_p, const float2 *p, const float2 *vel,
+                               const Geo &g, float dt, bool no_slip, int *status);
+int launch_advect_rgb_gather(const Launch &L, uint32_t *next_c, const uint32_t *c, const float2 *vel,
+                             const Geo &g, float dt, bool no_slip, int *status);
+
+// stencil.cu — finitediff.cpp:9-82, ino:264-269
+int launch_divergence(const Launch &L, float *div, const float2 *v, const Geo &g, float dx);
+int launch_subtract_gradient(const Launch &L, float2 *v_out, const float2 *v_in, const float *p,
+                             const Geo &g, float dx);
+int launch_apply_drags(const Launch &L, float2 *v, const fs_drag *drags_host, int n, const Geo &g);
+int launch_max_displacement(const Launch &L, unsigned int *out_bits, const float2 *vel, const Geo &g);
+
+// sor.cu — poisson.cpp:14-125
+int launch_sor_half_sweep(const Launch &L, float *p, const float *div, const Geo &g, float dx,
+                          float omega, int parity);
+
+// upscale.cu — ino:116-177
+int launch_upscale4_rgb565(const Launch &L, uint16_t *out, const uint32_t *c, int dim_x, int dim_y);
+
+}  // namespace fs

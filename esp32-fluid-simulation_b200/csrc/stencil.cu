@@ -1,0 +1,157 @@
+// Finite-difference stencils with the wall handling fused in
+// (finitediff.cpp:9-82), the drag overwrite (ino:264-269) and the max-
+// displacement reduction that sizes advect halos on decomposed grids.
+//
+// domain_iter (operations.h:11-38) splits a grid into an interior that gets
+// `expr_fast` and four edges that get `expr_safe`.  The GPU analogue is a
+// per-thread wall test on GLOBAL coordinates: interior threads take the fast
+// expression, wall threads the safe one — the two associate the sum
+// differently, and both orders are kept.
+#include "kernels.h"
+
+namespace fs {
+
+constexpr int ST_BX = 64, ST_BY = 4;
+
+// calculate_divergence, finitediff.cpp:33-39
+__global__ void __launch_bounds__(ST_BX *ST_BY)
+divergence_kernel(float *__restrict__ div, const float2 *__restrict__ v, Geo g, float two_dx_inv)
+{
+    const int lx = g.x0 + blockIdx.x * ST_BX + threadIdx.x;
+    const int ly = g.y0 + blockIdx.y * ST_BY + threadIdx.y;
+    if (lx >= g.x1 || ly >= g.y1) return;
+    const size_t l = (size_t)ly * g.nx + lx;
+    const int gi = g.ox + lx, gj = g.oy + ly;
+    const int i_max = g.GX - 1, j_max = g.GY - 1;
+    const bool wall = gi == 0 || gi == i_max || gj == 0 || gj == j_max;
+    float s;
+    if (!wall) {  // div_expr_fast, finitediff.cpp:29: (-L.x + R.x) + (-D.y + U.y)
+        const float lxv = __ldg(&v[l - 1].x), rxv = __ldg(&v[l + 1].x);
+        const float dyv = __ldg(&v[l - g.nx].y), uyv = __ldg(&v[l + g.nx].y);
+        s = __fadd_rn(__fadd_rn(-lxv, rxv), __fadd_rn(-dyv, uyv));
+    } else {      // div_expr_safe, finitediff.cpp:16-20: ghost velocity is the negated wall node
+        const float2 c = __ldg(&v[l]);
+        s = 0.0f;
+        s = __fadd_rn(s, gi > 0 ? -__ldg(&v[l - 1].x) : c.x);
+        s = __fadd_rn(s, gi < i_max ? __ldg(&v[l + 1].x) : -c.x);
+        s = __fadd_rn(s, gj > 0 ? -__ldg(&v[l - g.nx].y) : c.y);
+        s = __fadd_rn(s, gj < j_max ? __ldg(&v[l + g.nx].y) : -c.y);
+    }
+    div[l] = __fmul_rn(s, two_dx_inv);
+}
+
+// subtract_gradient, finitediff.cpp:41-82 (in place: only v[ij] itself is read)
+__global__ void __launch_bounds__(ST_BX *ST_BY)
+subtract_gradient_kernel(float2 *v_out, const float2 *v_in, const float *__restrict__ p, Geo g,
+                         float two_dx_inv)
+{
+    const int lx = g.x0 + blockIdx.x * ST_BX + threadIdx.x;
+    const int ly = g.y0 + blockIdx.y * ST_BY + threadIdx.y;
+    if (lx >= g.x1 || ly >= g.y1) return;
+    const size_t l = (size_t)ly * g.nx + lx;
+    const int gi = g.ox + lx, gj = g.oy + ly;
+    const float pc = __ldg(&p[l]);
+    // a missing neighbour is replaced by the node's own pressure (finitediff.cpp:51-54)
+    const float pl = gi > 0 ? __ldg(&p[l - 1]) : pc;
+    const float pr = gi < g.GX - 1 ? __ldg(&p[l + 1]) : pc;
+    const float pd = gj > 0 ? __ldg(&p[l - g.nx]) : pc;
+    const float pu = gj < g.GY - 1 ? __ldg(&p[l + g.nx]) : pc;
+    const float gx = __fmul_rn(__fsub_rn(pr, pl), two_dx_inv);
+    const float gy = __fmul_rn(__fsub_rn(pu, pd), two_dx_inv);
+    float2 c = v_in[l];  // v_out may alias v_in (the reference runs in place, finitediff.cpp:80)
+    c.x = __fsub_rn(c.x, gx);
+    c.y = __fsub_rn(c.y, gy);
+    v_out[l] = c;
+}
+
+// Drag overwrite, ino:264-269.  The queue is drained IN ORDER and each record
+// SETS one node, so a later record wins: one thread replays the list.  Records
+// travel as kernel parameters (no staging copy; at most DRAG_CHUNK per launch).
+constexpr int DRAG_CHUNK = 128;
+struct DragChunk {
+    fs_drag d[DRAG_CHUNK];
+};
+
+__global__ void apply_drags_kernel(float2 *__restrict__ v, DragChunk chunk, int n, Geo g)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int k = 0; k < n; k++) {
+        const fs_drag m = chunk.d[k];
+        // index(coords.y, coords.x, N_ROWS): coords.y runs along the fast axis
+        const int gi = m.cy, gj = m.cx;
+        if (gi >= g.GX || gj >= g.GY) continue;  // reference: out-of-bounds write
+        const int lx = gi - g.ox, ly = gj - g.oy;
+        if (lx < g.x0 || lx >= g.x1 || ly < g.y0 || ly >= g.y1) continue;  // another rank's node
+        v[(size_t)ly * g.nx + lx] = make_float2(m.vy, m.vx);  // swapped, ino:267
+    }
+}
+
+// max over the rectangle of max(|v.x|,|v.y|) as float bits (non-negative floats
+// order like unsigned ints); NaN is ignored.
+__global__ void __launch_bounds__(256)
+max_displacement_kernel(unsigned int *__restrict__ out_bits, const float2 *__restrict__ vel, Geo g)
+{
+    const int w = g.x1 - g.x0, h = g.y1 - g.y0;
+    const size_t n = (size_t)w * h;
+    float m = 0.0f;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+         k += (size_t)gridDim.x * blockDim.x) {
+        const int lx = g.x0 + (int)(k % w), ly = g.y0 + (int)(k / w);
+        const float2 c = __ldg(&vel[(size_t)ly * g.nx + lx]);
+        m = fmaxf(m, fmaxf(fabsf(c.x), fabsf(c.y)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
+}
+
+static inline dim3 st_grid(const Geo &g)
+{
+    return dim3((g.x1 - g.x0 + ST_BX - 1) / ST_BX, (g.y1 - g.y0 + ST_BY - 1) / ST_BY);
+}
+
+int launch_divergence(const Launch &L, float *div, const float2 *v, const Geo &g, float dx)
+{
+    if (g.x1 <= g.x0 || g.y1 <= g.y0) return 0;
+    const float two_dx_inv = 1.0f / (2.0f * dx);  // finitediff.cpp:36, formed on the host in float
+    divergence_kernel<<<st_grid(g), dim3(ST_BX, ST_BY), 0, L.stream>>>(div, v, g, two_dx_inv);
+    ++*L.launches;
+    return (int)cudaGetLastError();
+}
+
+int launch_subtract_gradient(const Launch &L, float2 *v_out, const float2 *v_in, const float *p,
+                             const Geo &g, float dx)
+{
+    if (g.x1 <= g.x0 || g.y1 <= g.y0) return 0;
+    const float two_dx_inv = 1.0f / (2.0f * dx);  // finitediff.cpp:79
+    subtract_gradient_kernel<<<st_grid(g), dim3(ST_BX, ST_BY), 0, L.stream>>>(v_out, v_in, p, g,
+                                                                              two_dx_inv);
+    ++*L.launches;
+    return (int)cudaGetLastError();
+}
+
+int launch_apply_drags(const Launch &L, float2 *v, const fs_drag *drags_host, int n, const Geo &g)
+{
+    for (int base = 0; base < n; base += DRAG_CHUNK) {
+        DragChunk chunk;
+        const int m = n - base < DRAG_CHUNK ? n - base : DRAG_CHUNK;
+        for (int k = 0; k < m; k++) chunk.d[k] = drags_host[base + k];
+        apply_drags_kernel<<<1, 32, 0, L.stream>>>(v, chunk, m, g);
+        ++*L.launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+
+int launch_max_displacement(const Launch &L, unsigned int *out_bits, const float2 *vel, const Geo &g)
+{
+    cudaError_t e = cudaMemsetAsync(out_bits, 0, sizeof(unsigned int), L.stream);
+    if (e != cudaSuccess) return (int)e;
+    if (g.x1 <= g.x0 || g.y1 <= g.y0) return 0;
+    max_displacement_kernel<<<L.num_sms * 4, 256, 0, L.stream>>>(out_bits, vel, g);
+    ++*L.launches;
+    return (int)cudaGetLastError();
+}
+
+}  // namespace fs

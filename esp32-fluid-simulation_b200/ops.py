@@ -1,0 +1,290 @@
+"""Host-side mirror of the reference's sim-step operator surface.
+
+Same names, argument order and meaning as the reference's free functions
+(advect.h:74-76, finitediff.h:6-10, poisson.h:4-5), so parity tests read like
+calls into the reference:
+
+    advect(next_p, p, vel, dim_x, dim_y, dt, no_slip)
+    calculate_divergence(div, v, dim_x, dim_y, dx)
+    subtract_gradient(v, p, dim_x, dim_y, dx)
+    poisson_solve(p, div, dim_x, dim_y, dx, iters, omega)
+
+Arrays are caller-owned, dense, in the reference layout (ij = dim_x*j + i).
+torch CUDA tensors go through the device-pointer entry points (``fs_*``,
+asynchronous on the context's stream); numpy arrays go through the host-pointer
+drop-ins (``fsh_*``: copy in, same kernels, copy out).  ``advect`` dispatches on
+the payload type like the reference's template: float32 -> Vector2<float>,
+uint32 -> Vector3<UQ32>.
+
+torch is used for device memory and streams only; no torch op is on the path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Tile, check
+
+DRAG_DTYPE = np.dtype([("cx", "<u2"), ("cy", "<u2"), ("vx", "<f4"), ("vy", "<f4")])  # ino:45-48
+
+
+def _is_torch(a) -> bool:
+    return type(a).__module__.startswith("torch")
+
+
+def _ptr(a, dtype_name: str, n_elems: int | None = None) -> tuple[int, bool]:
+    """(address, on_device).  Validates dtype / contiguity / device."""
+    if a is None:
+        return 0, False
+    if _is_torch(a):
+        import torch
+        want = {"float32": torch.float32, "uint32": torch.uint32, "int32": torch.int32,
+                "uint16": torch.uint16, "int16": torch.int16}[dtype_name]
+        alt = {"uint32": torch.int32, "uint16": torch.int16}.get(dtype_name)
+        if a.dtype != want and a.dtype != alt:
+            raise TypeError(f"expected {dtype_name} tensor, got {a.dtype}")
+        if not a.is_contiguous():
+            raise ValueError("tensor must be contiguous (dense reference layout)")
+        if n_elems is not None and a.numel() < n_elems:
+            raise ValueError(f"tensor has {a.numel()} elements, need {n_elems}")
+        if not a.is_cuda:
+            return a.data_ptr(), False
+        return a.data_ptr(), True
+    if not isinstance(a, np.ndarray):
+        raise TypeError(f"unsupported array type {type(a)}")
+    if a.dtype != np.dtype(dtype_name):
+        raise TypeError(f"expected {dtype_name} array, got {a.dtype}")
+    if not a.flags.c_contiguous:
+        raise ValueError("array must be C-contiguous (dense reference layout)")
+    if n_elems is not None and a.size < n_elems:
+        raise ValueError(f"array has {a.size} elements, need {n_elems}")
+    return a.ctypes.data, False
+
+
+def _payload(a) -> str:
+    if _is_torch(a):
+        import torch
+        return "vec2f" if a.dtype == torch.float32 else "rgb"
+    return "vec2f" if a.dtype == np.float32 else "rgb"
+
+
+def _drags(drags):
+    if drags is None:
+        return None, 0
+    d = np.ascontiguousarray(drags, DRAG_DTYPE)
+    return d, len(d)
+
+
+class Context:
+    """fs_ctx: device + stream + scratch.  ``stream`` is a ``torch.cuda.Stream``,
+    a raw ``cudaStream_t`` integer or None (legacy default stream)."""
+
+    def __init__(self, device: int = 0, stream=None):
+        self._L = _lib.lib()
+        handle = C.c_void_p()
+        s = 0
+        if stream is not None:
+            s = getattr(stream, "cuda_stream", stream)
+        check(self._L.fs_ctx_create(C.byref(handle), int(device), C.c_void_p(s)), "fs_ctx_create")
+        self._h = handle
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.fs_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(self._L.fs_ctx_synchronize(self._h), "fs_ctx_synchronize")
+
+    def set_option(self, name: str, value: int):
+        check(self._L.fs_ctx_set_option(self._h, name.encode(), int(value)), f"set_option({name})")
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int()
+        check(self._L.fs_ctx_get_option(self._h, name.encode(), C.byref(v)), f"get_option({name})")
+        return v.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.fs_ctx_launch_count(self._h))
+
+    # --- the reference's operator surface ------------------------------------------
+    def advect(self, next_p, p, vel, dim_x, dim_y, dt, no_slip):
+        n = dim_x * dim_y
+        kind = _payload(p)
+        dt_name, nc = ("float32", 2) if kind == "vec2f" else ("uint32", 3)
+        a_out, dev0 = _ptr(next_p, dt_name, n * nc)
+        a_in, dev1 = _ptr(p, dt_name, n * nc)
+        a_vel, dev2 = _ptr(vel, "float32", n * 2)
+        if not (dev0 == dev1 == dev2):
+            raise ValueError("advect: arrays must all be on the host or all on the device")
+        pre = "fs_" if dev0 else "fsh_"
+        fn = getattr(self._L, pre + ("advect_vec2f" if kind == "vec2f" else "advect_rgb_uq32"))
+        check(fn(a_out, a_in, a_vel, dim_x, dim_y, dt, int(bool(no_slip)), self._h), fn.__name__)
+
+    def calculate_divergence(self, div, v, dim_x, dim_y, dx):
+        n = dim_x * dim_y
+        a_div, d0 = _ptr(div, "float32", n)
+        a_v, d1 = _ptr(v, "float32", 2 * n)
+        if d0 != d1:
+            raise ValueError("calculate_divergence: mixed host/device arrays")
+        fn = self._L.fs_calculate_divergence if d0 else self._L.fsh_calculate_divergence
+        check(fn(a_div, a_v, dim_x, dim_y, dx, self._h), "calculate_divergence")
+
+    def subtract_gradient(self, v, p, dim_x, dim_y, dx):
+        n = dim_x * dim_y
+        a_v, d0 = _ptr(v, "float32", 2 * n)
+        a_p, d1 = _ptr(p, "float32", n)
+        if d0 != d1:
+            raise ValueError("subtract_gradient: mixed host/device arrays")
+        fn = self._L.fs_subtract_gradient if d0 else self._L.fsh_subtract_gradient
+        check(fn(a_v, a_p, dim_x, dim_y, dx, self._h), "subtract_gradient")
+
+    def poisson_solve(self, p, div, dim_x, dim_y, dx, iters, omega):
+        n = dim_x * dim_y
+        a_p, d0 = _ptr(p, "float32", n)
+        a_d, d1 = _ptr(div, "float32", n)
+        if d0 != d1:
+            raise ValueError("poisson_solve: mixed host/device arrays")
+        fn = self._L.fs_poisson_solve if d0 else self._L.fsh_poisson_solve
+        check(fn(a_p, a_d, dim_x, dim_y, dx, iters, omega, self._h), "poisson_solve")
+
+    # --- the rest of loop() ------------------------------------------------------------
+    def sor_half_sweep(self, p, div, dim_x, dim_y, dx, omega, parity):
+        n = dim_x * dim_y
+        a_p, d0 = _ptr(p, "float32", n)
+        a_d, d1 = _ptr(div, "float32", n)
+        if not (d0 and d1):
+            raise ValueError("sor_half_sweep: device tensors only")
+        check(self._L.fs_sor_half_sweep(a_p, a_d, dim_x, dim_y, dx, omega, parity, self._h),
+              "fs_sor_half_sweep")
+
+    def apply_drags(self, v, drags, dim_x, dim_y):
+        a_v, d0 = _ptr(v, "float32", 2 * dim_x * dim_y)
+        if not d0:
+            raise ValueError("apply_drags: v must be a device tensor")
+        d, n = _drags(drags)
+        check(self._L.fs_apply_drags(a_v, d.ctypes.data if n else None, n, dim_x, dim_y, self._h),
+              "fs_apply_drags")
+
+    def step(self, v, c, drags, dim_x, dim_y, dt, dx, iters, omega, p_out=None, div_out=None):
+        """loop() body (ino:249-289), in place on v and c."""
+        n = dim_x * dim_y
+        a_v, d0 = _ptr(v, "float32", 2 * n)
+        a_c, d1 = _ptr(c, "uint32", 3 * n)
+        a_p, d2 = _ptr(p_out, "float32", n)
+        a_d, d3 = _ptr(div_out, "float32", n)
+        if d0 != d1 or (p_out is not None and d2 != d0) or (div_out is not None and d3 != d0):
+            raise ValueError("step: mixed host/device arrays")
+        d, nd = _drags(drags)
+        fn = self._L.fs_step if d0 else self._L.fsh_step
+        check(fn(a_v, a_c, d.ctypes.data if nd else None, nd, dim_x, dim_y, dt, dx, iters, omega,
+                 a_p or None, a_d or None, self._h), "step")
+
+    def upscale4_rgb565(self, out, c, dim_x, dim_y):
+        a_o, d0 = _ptr(out, "uint16", 16 * (dim_x - 1) * (dim_y - 1))
+        a_c, d1 = _ptr(c, "uint32", 3 * dim_x * dim_y)
+        if d0 != d1:
+            raise ValueError("upscale4_rgb565: mixed host/device arrays")
+        fn = self._L.fs_upscale4_rgb565 if d0 else self._L.fsh_upscale4_rgb565
+        check(fn(a_o, a_c, dim_x, dim_y, self._h), "upscale4_rgb565")
+
+    def ensemble_step(self, v, c, batch, dim_x, dim_y, dt, dx, iters, omega, n_steps=1,
+                      drags=None, drag_counts=None, max_drags=0):
+        n = batch * dim_x * dim_y
+        a_v, d0 = _ptr(v, "float32", 2 * n)
+        a_c, d1 = _ptr(c, "uint32", 3 * n)
+        if not (d0 and d1):
+            raise ValueError("ensemble_step: device tensors only")
+        dptr = cptr = None
+        if max_drags > 0:
+            d = np.ascontiguousarray(drags, DRAG_DTYPE)
+            cnt = np.ascontiguousarray(drag_counts, np.int32)
+            assert d.size == batch * max_drags and cnt.size == batch
+            dptr, cptr = d.ctypes.data, cnt.ctypes.data
+        check(self._L.fs_ensemble_step(a_v, a_c, dptr, cptr, max_drags, batch, dim_x, dim_y, dt, dx,
+                                       iters, omega, n_steps, self._h), "fs_ensemble_step")
+
+    # --- decomposed grids ----------------------------------------------------------------
+    def tile_advect(self, next_p, p, vel, tile: Tile, dt, no_slip):
+        kind = _payload(p)
+        dt_name = "float32" if kind == "vec2f" else "uint32"
+        fn = self._L.fs_tile_advect_vec2f if kind == "vec2f" else self._L.fs_tile_advect_rgb_uq32
+        check(fn(_ptr(next_p, dt_name)[0], _ptr(p, dt_name)[0], _ptr(vel, "float32")[0],
+                 C.byref(tile), dt, int(bool(no_slip)), self._h), "fs_tile_advect")
+
+    def tile_calculate_divergence(self, div, v, tile: Tile, dx):
+        check(self._L.fs_tile_calculate_divergence(_ptr(div, "float32")[0], _ptr(v, "float32")[0],
+                                                   C.byref(tile), dx, self._h),
+              "fs_tile_calculate_divergence")
+
+    def tile_subtract_gradient(self, v, p, tile: Tile, dx):
+        check(self._L.fs_tile_subtract_gradient(_ptr(v, "float32")[0], _ptr(p, "float32")[0],
+                                                C.byref(tile), dx, self._h),
+              "fs_tile_subtract_gradient")
+
+    def tile_sor_sweeps(self, p_out, p_in, div, tile: Tile, dx, omega, first_parity, n_half):
+        check(self._L.fs_tile_sor_sweeps(_ptr(p_out, "float32")[0],
+                                         _ptr(p_in, "float32")[0] or None,
+                                         _ptr(div, "float32")[0], C.byref(tile), dx, omega,
+                                         first_parity, n_half, self._h), "fs_tile_sor_sweeps")
+
+    def tile_apply_drags(self, v, drags, tile: Tile):
+        d, n = _drags(drags)
+        check(self._L.fs_tile_apply_drags(_ptr(v, "float32")[0], d.ctypes.data if n else None, n,
+                                          C.byref(tile), self._h), "fs_tile_apply_drags")
+
+    def tile_check(self):
+        check(self._L.fs_tile_check(self._h), "fs_tile_check")
+
+    def tile_max_displacement(self, vel, tile: Tile, dt) -> int:
+        out = C.c_int()
+        check(self._L.fs_tile_max_displacement(C.byref(out), _ptr(vel, "float32")[0], C.byref(tile),
+                                               dt, self._h), "fs_tile_max_displacement")
+        return out.value
+
+
+# ---- module-level functions with the reference's exact names -------------------------
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def _ctx_for(a, ctx):
+    if ctx is not None:
+        return ctx
+    dev = a.device.index if _is_torch(a) and a.is_cuda else 0
+    return default_context(dev or 0)
+
+
+def advect(next_p, p, vel, dim_x, dim_y, dt, no_slip, ctx: Context | None = None):
+    """advect<T,U>, advect.h:74-85."""
+    _ctx_for(p, ctx).advect(next_p, p, vel, dim_x, dim_y, dt, no_slip)
+
+
+def calculate_divergence(div, v, dim_x, dim_y, dx, ctx: Context | None = None):
+    """calculate_divergence, finitediff.cpp:33-39."""
+    _ctx_for(v, ctx).calculate_divergence(div, v, dim_x, dim_y, dx)
+
+
+def subtract_gradient(v, p, dim_x, dim_y, dx, ctx: Context | None = None):
+    """subtract_gradient, finitediff.cpp:75-82 (v in place)."""
+    _ctx_for(v, ctx).subtract_gradient(v, p, dim_x, dim_y, dx)
+
+
+def poisson_solve(p, div, dim_x, dim_y, dx, iters, omega, ctx: Context | None = None):
+    """poisson_solve, poisson.cpp:114-125."""
+    _ctx_for(p, ctx).poisson_solve(p, div, dim_x, dim_y, dx, iters, omega)

@@ -1,0 +1,180 @@
+/* fluid_b200.h — C ABI of the B200-native stable-fluids step.
+ *
+ * Drop-in boundary for the sim-step operators of colonelwatch/ESP32-fluid-
+ * simulation.  The reference has no FFI layer; its de-facto boundary is five
+ * free functions over caller-owned dense arrays, called only from loop()
+ * (ESP32-fluid-simulation.ino:249-289).  Every entry point below names the
+ * reference interface it replaces.  Signatures keep the reference's argument
+ * order and meaning; the only additions are an `int` status return and a
+ * trailing opaque context (device + stream + scratch).
+ *
+ * Layout contract (identical to the reference, operations.h:7-9, vector.h,
+ * uq32.h): dense, unpadded, node (i,j) at ij = dim_x*j + i (i is the fast
+ * axis); velocity = {float x,y} (8 B), dye = {uint32 r,g,b} UQ32 raw words
+ * (12 B, align 4), scalars = float.  Caller allocates and frees everything.
+ *
+ *   fs_*   : pointers are DEVICE pointers; work is enqueued on the context's
+ *            stream and the call returns without synchronising.
+ *   fsh_*  : pointers are HOST pointers (what reference code holds today); the
+ *            call copies in, runs the same kernels, copies out and returns when
+ *            the result is in host memory — a literal drop-in for the reference
+ *            call of the same name.
+ *
+ * Results are bit-identical to the reference compiled with FMA contraction off
+ * (g++ -O2 -ffp-contract=off), for floats as well as for UQ32 words.  The one
+ * defined deviation: float->UQ32 conversion SATURATES (>= 2^32 -> 0xFFFFFFFF,
+ * negative/NaN -> 0) where uq32.h:13 is undefined behaviour.
+ *
+ * There is no CPU fallback: every call fails with a CUDA error code when no
+ * sm_100 device is usable.
+ */
+#ifndef FLUID_B200_H
+#define FLUID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS_OK 0
+#define FS_ERR_INVALID_ARG (-1)   /* NULL pointer, dim < 2, iters < 0, aliasing violation */
+#define FS_ERR_NO_CONTEXT (-2)
+#define FS_ERR_UNSUPPORTED (-3)
+#define FS_ERR_HALO_OVERRUN (-4)  /* decomposed advect: backtrace left the local window */
+/* positive values are cudaError_t codes */
+
+typedef struct fs_vec2f { float x, y; } fs_vec2f;             /* Vector2<float>, vector.h:4-57 */
+typedef struct fs_rgb_uq32 { uint32_t r, g, b; } fs_rgb_uq32; /* Vector3<UQ32>, vector.h:63-122 + uq32.h:8-16 */
+typedef struct fs_drag {                                      /* struct drag, ino:45-48 */
+    uint16_t cx, cy;   /* coords.x = column (slow axis j), coords.y = row (fast axis i) */
+    float vx, vy;      /* velocity.x, velocity.y in the graphics frame (swapped on apply) */
+} fs_drag;
+
+typedef struct fs_ctx fs_ctx;   /* opaque: device, stream, scratch buffers, TMA descriptors */
+
+/* ---- context -------------------------------------------------------------- */
+/* `stream` is a cudaStream_t (NULL = the legacy default stream). */
+int  fs_ctx_create(fs_ctx **out, int device, void *stream);
+int  fs_ctx_destroy(fs_ctx *ctx);
+int  fs_ctx_synchronize(fs_ctx *ctx);
+/* Kernel-variant switches for A/B measurement (all variants are bit-identical):
+ *   "sor"    : 0 = one half-sweep per launch, 1 = shared-memory temporally blocked (default)
+ *   "sor_t"  : full iterations fused per HBM round trip (1..8, default 4)
+ *   "advect" : 0 = direct L1/L2 gather, 1 = TMA-staged shared-memory tile (default where legal)
+ *   "fuse"   : 0 = fs_step runs the operators one by one, 1 = divergence/gradient fused into SOR passes */
+int  fs_ctx_set_option(fs_ctx *ctx, const char *name, int value);
+int  fs_ctx_get_option(fs_ctx *ctx, const char *name, int *value);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+uint64_t fs_ctx_launch_count(fs_ctx *ctx);
+const char *fs_version(void);
+const char *fs_error_string(int code);
+
+/* pinned host memory for the fsh_* path / harness */
+int  fs_host_alloc(void **out, size_t bytes);
+int  fs_host_free(void *p);
+
+/* ---- sim-step operators, device pointers ----------------------------------- */
+/* advect<Vector2<float>,float>, advect.h:74-85 (ino:253).  next_p must not alias p/vel; p may alias vel. */
+int fs_advect_vec2f(fs_vec2f *next_p, const fs_vec2f *p, const fs_vec2f *vel,
+                    int dim_x, int dim_y, float dt, int no_slip, fs_ctx *ctx);
+/* advect<Vector3<UQ32>,float>, advect.h:74-85 (ino:282). */
+int fs_advect_rgb_uq32(fs_rgb_uq32 *next_c, const fs_rgb_uq32 *c, const fs_vec2f *vel,
+                       int dim_x, int dim_y, float dt, int no_slip, fs_ctx *ctx);
+/* calculate_divergence, finitediff.h:6-7 / finitediff.cpp:33-39. */
+int fs_calculate_divergence(float *div, const fs_vec2f *v, int dim_x, int dim_y,
+                            float dx, fs_ctx *ctx);
+/* subtract_gradient, finitediff.h:9-10 / finitediff.cpp:75-82 (v in place). */
+int fs_subtract_gradient(fs_vec2f *v, const float *p, int dim_x, int dim_y, float dx,
+                         fs_ctx *ctx);
+/* poisson_solve, poisson.h:4-5 / poisson.cpp:114-125 (p overwritten from zero; p != div). */
+int fs_poisson_solve(float *p, const float *div, int dim_x, int dim_y, float dx,
+                     int iters, float omega, fs_ctx *ctx);
+/* one colour of domain_iter_red_black, poisson.cpp:14-61 (parity 0 = (i+j) even = the reference's first pass). */
+int fs_sor_half_sweep(float *p, const float *div, int dim_x, int dim_y, float dx,
+                      float omega, int parity, fs_ctx *ctx);
+/* drag overwrite, ino:264-269.  `drags` is a HOST array (it is the touch queue);
+ * records outside the grid are dropped (the reference writes out of bounds). */
+int fs_apply_drags(fs_vec2f *v, const fs_drag *drags, int n, int dim_x, int dim_y,
+                   fs_ctx *ctx);
+/* loop() body, ino:249-289: advect v (no-slip) -> drags -> divergence -> SOR ->
+ * gradient-subtract -> advect dye (free-slip).  v and c are updated in place.
+ * p_out/div_out (dim_x*dim_y floats each, device) receive the step's pressure
+ * and divergence, or may be NULL. */
+int fs_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags, int n_drags,
+            int dim_x, int dim_y, float dt, float dx, int iters, float omega,
+            float *p_out, float *div_out, fs_ctx *ctx);
+/* draw_routine arithmetic, ino:116-177: 4x bilinear upscale of the dye, UQ32
+ * round, RGB565 pack, byte swap.  out is (dim_x-1)*4 rows x (dim_y-1)*4 columns
+ * of uint16, row pitch (dim_y-1)*4 (image rows run along the sim's fast axis). */
+int fs_upscale4_rgb565(uint16_t *out, const fs_rgb_uq32 *c, int dim_x, int dim_y,
+                       fs_ctx *ctx);
+/* `batch` independent grids, each a full loop() body, one CTA per grid with the
+ * grid resident in shared memory (BASELINE.json configs[1]).  v, c hold the
+ * grids back to back.  drags: host array of batch*max_drags records, drag_counts:
+ * host array of `batch` counts (both may be NULL with max_drags = 0). */
+int fs_ensemble_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags,
+                     const int *drag_counts, int max_drags, int batch, int dim_x,
+                     int dim_y, float dt, float dx, int iters, float omega,
+                     int n_steps, fs_ctx *ctx);
+
+/* ---- the same operators over HOST pointers (reference drop-ins) ------------- */
+int fsh_advect_vec2f(fs_vec2f *next_p, const fs_vec2f *p, const fs_vec2f *vel,
+                     int dim_x, int dim_y, float dt, int no_slip, fs_ctx *ctx);
+int fsh_advect_rgb_uq32(fs_rgb_uq32 *next_c, const fs_rgb_uq32 *c, const fs_vec2f *vel,
+                        int dim_x, int dim_y, float dt, int no_slip, fs_ctx *ctx);
+int fsh_calculate_divergence(float *div, const fs_vec2f *v, int dim_x, int dim_y,
+                             float dx, fs_ctx *ctx);
+int fsh_subtract_gradient(fs_vec2f *v, const float *p, int dim_x, int dim_y, float dx,
+                          fs_ctx *ctx);
+int fsh_poisson_solve(float *p, const float *div, int dim_x, int dim_y, float dx,
+                      int iters, float omega, fs_ctx *ctx);
+int fsh_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags, int n_drags,
+             int dim_x, int dim_y, float dt, float dx, int iters, float omega,
+             float *p_out, float *div_out, fs_ctx *ctx);
+int fsh_upscale4_rgb565(uint16_t *out, const fs_rgb_uq32 *c, int dim_x, int dim_y,
+                        fs_ctx *ctx);
+
+/* ---- decomposed grids (2-D block decomposition) -------------- */
+/* A rank's padded local window of a global grid.  Local array element (lx,ly)
+ * lives at ly*nx + lx and is global node (ox+lx, oy+ly).  Wall rules apply only
+ * where the window touches the GLOBAL boundary; red/black parity and advect
+ * coordinates are global. */
+typedef struct fs_tile {
+    int gdim_x, gdim_y;   /* global grid */
+    int ox, oy;           /* global coordinate of local (0,0); may be negative only if clipped by caller */
+    int nx, ny;           /* local (padded) extents; pitch = nx */
+    int x0, y0, x1, y1;   /* compute rectangle [x0,x1) x [y0,y1) in local coordinates */
+} fs_tile;
+
+int fs_tile_advect_vec2f(fs_vec2f *next_p, const fs_vec2f *p, const fs_vec2f *vel,
+                         const fs_tile *t, float dt, int no_slip, fs_ctx *ctx);
+int fs_tile_advect_rgb_uq32(fs_rgb_uq32 *next_c, const fs_rgb_uq32 *c, const fs_vec2f *vel,
+                            const fs_tile *t, float dt, int no_slip, fs_ctx *ctx);
+int fs_tile_calculate_divergence(float *div, const fs_vec2f *v, const fs_tile *t,
+                                 float dx, fs_ctx *ctx);
+int fs_tile_subtract_gradient(fs_vec2f *v, const float *p, const fs_tile *t, float dx,
+                              fs_ctx *ctx);
+/* `n_half` consecutive half-sweeps starting with colour `first_parity`, from
+ * p_in to p_out (distinct buffers), valid on the compute rectangle provided
+ * p_in is valid on that rectangle grown by n_half nodes (clipped to the global
+ * grid).  p_in == NULL means "all zero" (poisson.cpp:117-119). */
+int fs_tile_sor_sweeps(float *p_out, const float *p_in, const float *div,
+                       const fs_tile *t, float dx, float omega, int first_parity,
+                       int n_half, fs_ctx *ctx);
+int fs_tile_apply_drags(fs_vec2f *v, const fs_drag *drags, int n, const fs_tile *t,
+                        fs_ctx *ctx);
+/* Reads (and clears) the context's device-side status flag set by tile advects
+ * whose backtrace left the local window: returns FS_OK or FS_ERR_HALO_OVERRUN.
+ * Synchronises the stream. */
+int fs_tile_check(fs_ctx *ctx);
+/* max over the compute rectangle of max(|v.x|,|v.y|)*dt, rounded up to whole
+ * nodes: the halo a subsequent advect needs.  Synchronises the stream. */
+int fs_tile_max_displacement(int *out_nodes, const fs_vec2f *vel, const fs_tile *t,
+                             float dt, fs_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUID_B200_H */

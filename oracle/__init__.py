@@ -1,0 +1,223 @@
+"""TEST INFRASTRUCTURE — ctypes loaders for the CPU checkers.
+
+  * ``Oracle``  -> oracle/libfluid_oracle.so  (plain-C restatement, fluid_oracle.c)
+  * ``Ref``     -> oracle/_ref/libfluid_ref.so (the reference's own sources, ref_shim.cpp)
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package.  The product package
+(``esp32-fluid-simulation_b200``) never does; it fails loudly without its CUDA
+library instead of falling back to anything here.
+
+Both classes expose the same method names over numpy arrays in the reference
+layout: velocity ``float32[dim_y, dim_x, 2]``, dye
+``uint32[dim_y, dim_x, 3]``, scalars ``float32[dim_y, dim_x]`` — i.e. node (i,j)
+at ``ij = dim_x*j + i`` (operations.h:7-9).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "libfluid_oracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libfluid_ref.so")
+REFERENCE_SRC = "/root/reference/ESP32-fluid-simulation"
+
+DRAG_DTYPE = np.dtype([("cx", "<u2"), ("cy", "<u2"), ("vx", "<f4"), ("vy", "<f4")])
+assert DRAG_DTYPE.itemsize == 12  # struct drag, ino:45-48
+
+
+def build(ref: bool | None = None) -> None:
+    """Compile the checkers (building the checker is not using it)."""
+    subprocess.run(["make", "-s", "-C", _HERE, "oracle"], check=True)
+    if ref is None:
+        ref = os.path.isdir(REFERENCE_SRC)
+    if ref:
+        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def _f32(a):
+    assert a.dtype == np.float32 and a.flags.c_contiguous, (a.dtype, a.flags)
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _u32(a):
+    assert a.dtype == np.uint32 and a.flags.c_contiguous, (a.dtype, a.flags)
+    return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+def _dims(a):
+    return int(a.shape[1]), int(a.shape[0])  # dim_x (fast), dim_y (slow)
+
+
+class _Base:
+    prefix = ""
+    path = ""
+
+    def __init__(self):
+        if not os.path.exists(self.path):
+            raise FileNotFoundError(f"{self.path} not built; run `make -C oracle`")
+        self.lib = C.CDLL(self.path)
+        L, p = self.lib, self.prefix
+        F, U, I, f = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_int, C.c_float
+        self._fn = {}
+        for name, args, res in [
+            ("advect_vec2f", [F, F, F, I, I, f, I], None),
+            ("advect_rgb_uq32", [U, U, F, I, I, f, I], None),
+            ("sample_vec2f", [F, F, f, f, I, I, I], None),
+            ("sample_rgb_uq32", [U, U, f, f, I, I, I], None),
+            ("uq32_from_float", [f], C.c_uint32),
+            ("uq32_to_float", [C.c_uint32], f),
+            ("calculate_divergence", [F, F, I, I, f], None),
+            ("subtract_gradient", [F, F, I, I, f], None),
+            ("poisson_solve", [F, F, I, I, f, I, f], None),
+            ("apply_drags", [F, C.c_void_p, I, I, I], None),
+            ("step", [F, U, C.c_void_p, I, I, I, f, f, I, f, F, F], None),
+        ]:
+            fn = getattr(L, p + name)
+            fn.argtypes, fn.restype = args, res
+            self._fn[name] = fn
+
+    # --- operators (same names as the reference's free functions) -------------
+    def advect_vec2f(self, p, vel, dt, no_slip=True):
+        dx_, dy_ = _dims(p)
+        out = np.empty_like(p)
+        self._fn["advect_vec2f"](_f32(out), _f32(p), _f32(vel), dx_, dy_, dt, int(no_slip))
+        return out
+
+    def advect_rgb_uq32(self, c, vel, dt, no_slip=False):
+        dx_, dy_ = _dims(c)
+        out = np.empty_like(c)
+        self._fn["advect_rgb_uq32"](_u32(out), _u32(c), _f32(vel), dx_, dy_, dt, int(no_slip))
+        return out
+
+    def sample_vec2f(self, p, i, j, no_slip):
+        dx_, dy_ = _dims(p)
+        out = np.empty(2, np.float32)
+        self._fn["sample_vec2f"](_f32(out), _f32(p), i, j, dx_, dy_, int(no_slip))
+        return out
+
+    def sample_rgb_uq32(self, c, i, j, no_slip):
+        dx_, dy_ = _dims(c)
+        out = np.empty(3, np.uint32)
+        self._fn["sample_rgb_uq32"](_u32(out), _u32(c), i, j, dx_, dy_, int(no_slip))
+        return out
+
+    def uq32_from_float(self, x):
+        return int(self._fn["uq32_from_float"](x))
+
+    def uq32_to_float(self, raw):
+        return float(self._fn["uq32_to_float"](raw))
+
+    def calculate_divergence(self, v, dx=1.0):
+        dx_, dy_ = _dims(v)
+        out = np.empty(v.shape[:2], np.float32)
+        self._fn["calculate_divergence"](_f32(out), _f32(v), dx_, dy_, dx)
+        return out
+
+    def subtract_gradient(self, v, p, dx=1.0):
+        """In place on ``v`` (finitediff.cpp:80); also returns it."""
+        dx_, dy_ = _dims(v)
+        self._fn["subtract_gradient"](_f32(v), _f32(p), dx_, dy_, dx)
+        return v
+
+    def poisson_solve(self, div, dx=1.0, iters=10, omega=1.96, p=None):
+        dx_, dy_ = _dims(div)
+        if p is None:
+            p = np.full(div.shape, 7.0, np.float32)  # initial contents must be ignored
+        self._fn["poisson_solve"](_f32(p), _f32(div), dx_, dy_, dx, iters, omega)
+        return p
+
+    def apply_drags(self, v, drags):
+        dx_, dy_ = _dims(v)
+        drags = np.ascontiguousarray(drags, DRAG_DTYPE)
+        self._fn["apply_drags"](_f32(v), drags.ctypes.data, len(drags), dx_, dy_)
+        return v
+
+    def step(self, v, c, drags=None, dt=1 / 30.0, dx=1.0, iters=10, omega=1.96,
+             want_fields=False):
+        """One loop() (ino:249-289), in place on v and c."""
+        dx_, dy_ = _dims(v)
+        if drags is None:
+            drags = np.zeros(0, DRAG_DTYPE)
+        drags = np.ascontiguousarray(drags, DRAG_DTYPE)
+        p = d = None
+        pp = dp = None
+        if want_fields:
+            p = np.empty(v.shape[:2], np.float32)
+            d = np.empty(v.shape[:2], np.float32)
+            pp, dp = _f32(p), _f32(d)
+        self._fn["step"](_f32(v), _u32(c), drags.ctypes.data, len(drags), dx_, dy_,
+                         dt, dx, iters, omega, pp, dp)
+        return (v, c, p, d) if want_fields else (v, c)
+
+
+class Oracle(_Base):
+    """Plain-C restatement (oracle/fluid_oracle.c)."""
+    prefix = "oracle_"
+    path = ORACLE_SO
+
+    def __init__(self):
+        super().__init__()
+        L = self.lib
+        F, U, I, f = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_int, C.c_float
+        L.oracle_sor_half_sweep.argtypes = [F, F, I, I, f, f, I]
+        L.oracle_sor_half_sweep.restype = None
+        L.oracle_upscale4_rgb565.argtypes = [C.POINTER(C.c_uint16), U, I, I]
+        L.oracle_upscale4_rgb565.restype = None
+        L.oracle_init_color_wheel.argtypes = [F, U, I, I]
+        L.oracle_init_color_wheel.restype = None
+        L.oracle_fnv1a64.argtypes = [C.c_void_p, C.c_uint64]
+        L.oracle_fnv1a64.restype = C.c_uint64
+
+    def sor_half_sweep(self, p, div, dx, omega, parity):
+        dx_, dy_ = _dims(p)
+        self.lib.oracle_sor_half_sweep(_f32(p), _f32(div), dx_, dy_, dx, omega, parity)
+        return p
+
+    def upscale4_rgb565(self, c):
+        dx_, dy_ = _dims(c)
+        out = np.empty(((dx_ - 1) * 4, (dy_ - 1) * 4), np.uint16)
+        self.lib.oracle_upscale4_rgb565(out.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                        _u32(c), dx_, dy_)
+        return out
+
+    def init_color_wheel(self, dim_x, dim_y):
+        v = np.empty((dim_y, dim_x, 2), np.float32)
+        c = np.empty((dim_y, dim_x, 3), np.uint32)
+        self.lib.oracle_init_color_wheel(_f32(v), _u32(c), dim_x, dim_y)
+        return v, c
+
+    def fnv1a64(self, a) -> int:
+        a = np.ascontiguousarray(a)
+        return int(self.lib.oracle_fnv1a64(a.ctypes.data, a.nbytes))
+
+
+class Ref(_Base):
+    """The reference's own sources behind ref_shim.cpp (oracle/_ref)."""
+    prefix = "ref_"
+    path = REF_SO
+
+    def __init__(self):
+        super().__init__()
+        L = self.lib
+        F, U, I = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_int
+        L.ref_saturates.restype = C.c_int
+        L.ref_fill_rand.argtypes = [F, U, I, I, C.c_uint]
+        L.ref_fill_rand.restype = None
+
+    def saturates(self) -> bool:
+        return bool(self.lib.ref_saturates())
+
+    def fill_rand(self, dim_x, dim_y, seed=1):
+        v = np.empty((dim_y, dim_x, 2), np.float32)
+        c = np.empty((dim_y, dim_x, 3), np.uint32)
+        self.lib.ref_fill_rand(_f32(v), _u32(c), dim_x, dim_y, seed)
+        return v, c
