@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric (BASELINE.json): Mcell-steps/s of the full stable-fluids step (advect v +
+drags + divergence + 50 red-black SOR iterations + gradient-subtract + advect
+dye) on a 4096x4096 grid; one "step" = one loop() body (ino:249-289) over the
+whole grid.  N>1 (torchrun, one rank per GPU): the grid is block-decomposed with
+4096x4096 nodes per GPU (weak scaling) and halos exchanged over NCCL.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` is
+the same step through the host-pointer drop-in fsh_step() with pinned host
+buffers (H2D + D2H inside the timed region); `roofline` is the SOR solve against
+the measured HBM copy peak; `cpu_baseline` is the reference's own C++ timed on
+this box's host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mcell-steps/s (advect+project, 50 SOR iters) at 4096^2"
+UNIT = "Mcell-steps/s"
+GRID = 4096          # per-GPU tile edge
+ITERS = 50
+N_DRAGS = 16
+SOR_BYTES_PER_NODE_ITER = 12.0     # read p + read d + write p per full iteration
+STEP_BYTES_PER_NODE = 80.0 + 12.0 * ITERS
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own C++ (oracle/_ref) on the host cores
+# ---------------------------------------------------------------------------------------------
+
+def cpu_impl():
+    import oracle
+    oracle.build()
+    if oracle.have_ref():
+        r = oracle.Ref()
+        if r.saturates():
+            return r, "reference"
+    return oracle.Oracle(), "port"
+
+
+def cpu_step_rate(dim_x, dim_y, steps, warmup):
+    """Mcell-steps/s of the single-threaded reference on a dim_x x dim_y grid."""
+    from esp32_fluid_simulation_b200 import synth
+    impl, kind = cpu_impl()
+    v = synth.velocity(GRID, GRID, window=(0, 0, dim_x, dim_y))
+    c = synth.dye(GRID, GRID, window=(0, 0, dim_x, dim_y))
+    times = []
+    for s in range(warmup + steps):
+        dr = synth.drags(dim_x, dim_y, s, n=N_DRAGS)
+        t0 = time.perf_counter()
+        impl.step(v, c, dr, synth.DT, synth.DX, ITERS, synth.OMEGA)
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return dim_x * dim_y * len(times) / total / 1e6, total / len(times), kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: a 4096 x 512 slab of the 4096^2 workload per step (~0.7 s of CPU each)
+    dim_x, dim_y = GRID, 512
+    rate, sec, kind = cpu_step_rate(dim_x, dim_y, args.steps, args.warmup)
+    sample = (f"each step = one full loop() body on a {dim_x}x{dim_y} slab of the {GRID}x{GRID} grid, "
+              f"K={ITERS}, {N_DRAGS} drags; single thread (the reference is single-threaded)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32+uq32", "data": "synthetic",
+        "config": {"workload": f"single {GRID}x{GRID} grid, {ITERS} SOR iterations, velocity + dye advection",
+                   "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import esp32_fluid_simulation_b200 as fb
+    from esp32_fluid_simulation_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if world > 1:
+        from esp32_fluid_simulation_b200 import dist as fdist
+        result = fdist.bench_decomposed(args, GRID, ITERS, N_DRAGS)
+    else:
+        result = bench_single(args, fb, synth, torch)
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_single(args, fb, synth, torch):
+    n = GRID
+    nodes = n * n
+    stream = torch.cuda.Stream()
+    ctx = fb.Context(0, stream)
+    v0, c0 = synth.velocity(n, n), synth.dye(n, n)
+    drags = [synth.drags(n, n, s, n=N_DRAGS) for s in range(args.warmup + args.steps)]
+    with torch.cuda.stream(stream):
+        dv = torch.from_numpy(v0).cuda()
+        dc = torch.from_numpy(c0.view(np.int32)).cuda()
+    stream.synchronize()
+
+    def step(s):
+        ctx.step(dv, dc, drags[s], n, n, synth.DT, synth.DX, ITERS, synth.OMEGA)
+
+    for s in range(args.warmup):
+        step(s)
+    stream.synchronize()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launch_count
+    with ClockSampler(0) as clk:
+        time.sleep(0.15)
+        ev0.record(stream)
+        for s in range(args.warmup, args.warmup + args.steps):
+            step(s)
+        ev1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        # keep the device busy a little longer so the sampler sees clocks under load
+        t_end = time.time() + 0.3
+        while time.time() < t_end:
+            step(args.warmup)
+        stream.synchronize()
+    launches = ctx.launch_count - launches0
+    ms = ev0.elapsed_time(ev1) / args.steps
+    value = nodes / (ms * 1e-3) / 1e6
+
+    # --- dominant kernel: the SOR solve, timed alone on the same stream ---
+    with torch.cuda.stream(stream):
+        dd = torch.randn(n, n, device="cuda") * 10
+        dp = torch.empty_like(dd)
+    for _ in range(2):
+        ctx.poisson_solve(dp, dd, n, n, synth.DX, ITERS, synth.OMEGA)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    l0 = ctx.launch_count
+    s0.record(stream)
+    for _ in range(reps):
+        ctx.poisson_solve(dp, dd, n, n, synth.DX, ITERS, synth.OMEGA)
+    s1.record(stream)
+    stream.synchronize()
+    sor_launches = (ctx.launch_count - l0) // reps
+    sor_ms = s0.elapsed_time(s1) / reps
+    peak, peak_src = measured_peaks()
+    achieved = SOR_BYTES_PER_NODE_ITER * nodes * ITERS / (sor_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "sor_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_solve")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "peak_source": peak_src,
+        "kernel": "SOR pressure solve (fs_poisson_solve: 50 red-black iterations, all launches of one solve)",
+        "algorithmic_bytes": SOR_BYTES_PER_NODE_ITER * nodes * ITERS,
+        "ms": sor_ms, "launches_per_solve": sor_launches,
+        "gnode_iters_per_s": nodes * ITERS / (sor_ms * 1e-3) / 1e9,
+        "step_frac": (STEP_BYTES_PER_NODE * nodes / (ms * 1e-3) / 1e9) / peak,
+        "sor_share_of_step": sor_ms / ms,
+    }
+
+    # --- e2e: the host-pointer drop-in fsh_step with pinned host buffers ---
+    hv = torch.from_numpy(v0.copy()).pin_memory()
+    hc = torch.from_numpy(c0.view(np.int32).copy()).pin_memory()
+    hv_np, hc_np = hv.numpy(), hc.numpy().view(np.uint32)
+    e2e_steps = max(3, min(args.steps, 10))
+    for s in range(2):
+        ctx.step(hv_np, hc_np, drags[s % len(drags)], n, n, synth.DT, synth.DX, ITERS, synth.OMEGA)
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        ctx.step(hv_np, hc_np, drags[s % len(drags)], n, n, synth.DT, synth.DX, ITERS, synth.OMEGA)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    state_bytes = nodes * (8 + 12)
+    e2e = {"value": nodes / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": state_bytes + 12 * N_DRAGS,
+           "d2h_bytes_per_step": state_bytes, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "api": "fsh_step (host pointers in, host pointers out; pinned buffers)"}
+
+    # --- cpu baseline beside it (bounded: 2 full-size steps, ~12 s) ---
+    cpu = None
+    if not args.no_cpu_baseline:
+        rate, sec, kind = cpu_step_rate(n, n, 2, 0)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"2 full steps of the same {n}x{n} K={ITERS} workload, single thread "
+                         f"({sec:.2f} s/step)"}
+
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32+uq32", "data": "synthetic",
+        "config": {"workload": f"single {n}x{n} grid, {ITERS} SOR iterations, velocity + dye advection",
+                   "grid": [n, n], "sor_iters": ITERS, "drags_per_step": N_DRAGS,
+                   "l2": "state (v 134 MB + dye 201 MB + p/div 134 MB) exceeds the 126 MB L2; no flush needed",
+                   "options": {k: ctx.get_option(k) for k in ("sor", "sor_t", "advect", "fuse")}},
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

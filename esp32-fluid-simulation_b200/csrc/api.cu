@@ -20,7 +20,7 @@ struct fs_ctx {
     size_t scratch_bytes[S_COUNT];
     int *status_dev;            // device flag raised by tile advects (FS_ERR_HALO_OVERRUN)
     unsigned int *maxdisp_dev;  // max-displacement reduction cell
-    int opt_sor, opt_sor_t, opt_advect, opt_fuse;
+    int opt_sor, opt_sor_t, opt_sor_shape, opt_advect, opt_fuse;
 };
 
 namespace {
@@ -119,6 +119,29 @@ int core_advect_rgb(fs_ctx *ctx, fs_rgb_uq32 *next_c, const fs_rgb_uq32 *c, cons
 int core_poisson_solve(fs_ctx *ctx, float *p, const float *div, const Geo &g, float dx, int iters,
                        float omega)
 {
+    if (ctx->opt_sor == 1 && iters > 0) {
+        // temporally blocked: T full iterations per HBM round trip, ping-ponging between p and a
+        // scratch buffer so that the LAST pass lands in the caller's p; pass 1 starts from zero
+        // without reading anything (poisson.cpp:117-119)
+        const int T = ctx->opt_sor_t;
+        const int passes = (iters + T - 1) / T;
+        void *scratch;
+        int e = ensure(ctx, S_P2, sizeof(float) * (size_t)g.nx * g.ny, &scratch);
+        if (e) return e;
+        float *bufs[2] = {(passes & 1) ? p : (float *)scratch, (passes & 1) ? (float *)scratch : p};
+        const float *src = nullptr;
+        int done = 0;
+        for (int k = 0; k < passes; k++) {
+            const int t = iters - done < T ? iters - done : T;
+            float *dst = bufs[k & 1];
+            if ((e = launch_sor_blocked(mk(ctx), dst, src, div, g, dx, omega, 0, 2 * t,
+                                        ctx->opt_sor_shape)))
+                return e;
+            src = dst;
+            done += t;
+        }
+        return FS_OK;
+    }
     FS_CUDA_TRY(cudaMemsetAsync(p, 0, sizeof(float) * (size_t)g.nx * g.ny, ctx->stream));
     for (int k = 0; k < iters; k++) {
         int e = launch_sor_half_sweep(mk(ctx), p, div, g, dx, omega, 0);
@@ -187,6 +210,7 @@ int fs_ctx_create(fs_ctx **out, int device, void *stream)
     ctx->num_sms = prop.multiProcessorCount;
     ctx->opt_sor = 1;
     ctx->opt_sor_t = 4;
+    ctx->opt_sor_shape = 0;
     ctx->opt_advect = 1;
     ctx->opt_fuse = 1;
     cudaError_t e = cudaMalloc(&ctx->status_dev, sizeof(int));
@@ -225,6 +249,7 @@ static int *opt_slot(fs_ctx *ctx, const char *name)
 {
     if (!strcmp(name, "sor")) return &ctx->opt_sor;
     if (!strcmp(name, "sor_t")) return &ctx->opt_sor_t;
+    if (!strcmp(name, "sor_shape")) return &ctx->opt_sor_shape;
     if (!strcmp(name, "advect")) return &ctx->opt_advect;
     if (!strcmp(name, "fuse")) return &ctx->opt_fuse;
     return nullptr;
@@ -576,6 +601,9 @@ int fs_tile_sor_sweeps(float *p_out, const float *p_in, const float *div, const 
         return FS_ERR_INVALID_ARG;
     DeviceGuard guard(ctx->device);
     const Geo g = geo_tile(*t);
+    if (ctx->opt_sor == 1 && n_half > 0 && n_half <= SOR_BLOCKED_MAX_HALF)
+        return launch_sor_blocked(mk(ctx), p_out, p_in, div, g, dx, omega, first_parity, n_half,
+                                  ctx->opt_sor_shape);
     // seed p_out on the rectangle grown by n_half, then sweep in place on
     // rectangles that shrink by one node per half-sweep
     const Geo seed = grown(g, n_half);

@@ -31,6 +31,12 @@ int launch_max_displacement(const Launch &L, unsigned int *out_bits, const float
 int launch_sor_half_sweep(const Launch &L, float *p, const float *div, const Geo &g, float dx,
                           float omega, int parity);
 
+// sor_blocked.cu — `n_half` colour half-sweeps per HBM round trip, p_in -> p_out (distinct
+// buffers; p_in == nullptr means all zero).  shape 0 = 128x96 region, 2 CTAs/SM; 1 = 128x192, 1 CTA/SM.
+constexpr int SOR_BLOCKED_MAX_HALF = 16;
+int launch_sor_blocked(const Launch &L, float *p_out, const float *p_in, const float *div, const Geo &g,
+                       float dx, float omega, int first_parity, int n_half, int shape);
+
 // upscale.cu — ino:116-177
 int launch_upscale4_rgb565(const Launch &L, uint16_t *out, const uint32_t *c, int dim_x, int dim_y);
 

@@ -1,0 +1,284 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes binding of
+include/fluid_b200.h), against the oracle on the same seeded inputs — BIT-EXACT
+for every field, floats included (tolerance 0 ulp; north_star allows 1e-5
+relative per step, the build is stricter)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_bit_equal
+from gpu_util import rand_drags, rand_fields, to_dev, to_host
+
+pytestmark = pytest.mark.gpu
+
+DT = np.float32(1 / 30.0)
+SHAPES = [(2, 2), (3, 2), (2, 5), (7, 3), (5, 4), (33, 17), (61, 81), (80, 60), (257, 129),
+          (130, 70), (512, 300), (1024, 512)]
+SOR_VARIANTS = [0, 1]
+
+
+@pytest.fixture(params=SOR_VARIANTS, ids=["sor=half-sweeps", "sor=blocked"])
+def sor_variant(request, ctx):
+    ctx.set_option("sor", request.param)
+    yield request.param
+    ctx.set_option("sor", 1)
+
+
+@pytest.fixture(params=[0, 1], ids=["advect=gather", "advect=tma"])
+def advect_variant(request, ctx):
+    ctx.set_option("advect", request.param)
+    yield request.param
+    ctx.set_option("advect", 1)
+
+
+# ---- per-operator parity -------------------------------------------------------------
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("no_slip", [1, 0])
+@pytest.mark.parametrize("vmax", [45.0, 400.0])
+def test_advect_velocity(ctx, oracle, advect_variant, shape, no_slip, vmax):
+    dim_x, dim_y = shape
+    v, _ = rand_fields(1, dim_x, dim_y, vmax)
+    dv, out = to_dev(v), torch.empty_like(to_dev(v))
+    ctx.advect(out, dv, dv, dim_x, dim_y, DT, no_slip)       # p aliases vel, as at ino:253
+    assert_bit_equal(to_host(out), oracle.advect_vec2f(v, v, DT, no_slip), "advect v")
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("no_slip", [0, 1])
+@pytest.mark.parametrize("vmax", [45.0, 400.0])
+def test_advect_dye(ctx, oracle, advect_variant, shape, no_slip, vmax):
+    dim_x, dim_y = shape
+    v, c = rand_fields(2, dim_x, dim_y, vmax)
+    dv, dc = to_dev(v), to_dev(c)
+    out = torch.empty_like(dc)
+    ctx.advect(out, dc, dv, dim_x, dim_y, DT, no_slip)
+    assert_bit_equal(to_host(out, np.uint32), oracle.advect_rgb_uq32(c, v, DT, no_slip), "advect dye")
+
+
+def test_advect_dye_saturation(ctx, oracle, advect_variant):
+    dim_x, dim_y = 96, 64
+    v, _ = rand_fields(3, dim_x, dim_y, 80.0)
+    c = np.full((dim_y, dim_x, 3), 0xFFFFFFFF, np.uint32)
+    c[::3, ::2] = 0xFFFFFF80
+    dc, dv = to_dev(c), to_dev(v)
+    out = torch.empty_like(dc)
+    ctx.advect(out, dc, dv, dim_x, dim_y, DT, 0)
+    got = to_host(out, np.uint32)
+    assert_bit_equal(got, oracle.advect_rgb_uq32(c, v, DT, 0), "saturating dye")
+    assert got.max() == 0xFFFFFFFF
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("dx", [1.0, 0.5, 3.0])
+def test_divergence_and_gradient(ctx, oracle, shape, dx):
+    dim_x, dim_y = shape
+    v, _ = rand_fields(4, dim_x, dim_y, 100.0)
+    dv = to_dev(v)
+    div = torch.empty(dim_y, dim_x, dtype=torch.float32, device="cuda")
+    ctx.calculate_divergence(div, dv, dim_x, dim_y, dx)
+    want_div = oracle.calculate_divergence(v, dx)
+    assert_bit_equal(to_host(div), want_div, "divergence")
+    p = np.random.default_rng(5).normal(0, 10, (dim_y, dim_x)).astype(np.float32)
+    ctx.subtract_gradient(dv, to_dev(p), dim_x, dim_y, dx)   # in place
+    assert_bit_equal(to_host(dv), oracle.subtract_gradient(v.copy(), p, dx), "gradient")
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("iters,omega,dx", [(10, 1.96, 1.0), (1, 1.0, 1.0), (7, 1.5, 2.0), (0, 1.96, 1.0),
+                                            (50, 1.96, 1.0)])
+def test_poisson_solve(ctx, oracle, sor_variant, shape, iters, omega, dx):
+    dim_x, dim_y = shape
+    d = np.random.default_rng(6).normal(0, 20, (dim_y, dim_x)).astype(np.float32)
+    p = torch.full((dim_y, dim_x), 7.0, dtype=torch.float32, device="cuda")  # must be ignored
+    ctx.poisson_solve(p, to_dev(d), dim_x, dim_y, dx, iters, omega)
+    assert_bit_equal(to_host(p), oracle.poisson_solve(d, dx, iters, omega), "pressure")
+
+
+@pytest.mark.parametrize("t_block", [1, 2, 3, 4, 6, 8])
+def test_poisson_solve_every_blocking_depth(ctx, oracle, t_block):
+    ctx.set_option("sor", 1)
+    ctx.set_option("sor_t", t_block)
+    try:
+        for dim_x, dim_y, iters in [(300, 200, 13), (61, 81, 10), (1000, 40, 9)]:
+            d = np.random.default_rng(7).normal(0, 20, (dim_y, dim_x)).astype(np.float32)
+            p = torch.empty(dim_y, dim_x, dtype=torch.float32, device="cuda")
+            ctx.poisson_solve(p, to_dev(d), dim_x, dim_y, 1.0, iters, 1.96)
+            assert_bit_equal(to_host(p), oracle.poisson_solve(d, 1.0, iters, 1.96), f"T={t_block}")
+    finally:
+        ctx.set_option("sor_t", 4)
+
+
+def test_half_sweep_colours(ctx, oracle):
+    dim_x, dim_y = 61, 81
+    rng = np.random.default_rng(8)
+    d = rng.normal(0, 5, (dim_y, dim_x)).astype(np.float32)
+    p = rng.normal(0, 5, (dim_y, dim_x)).astype(np.float32)
+    for parity in (0, 1):
+        dp = to_dev(p)
+        ctx.sor_half_sweep(dp, to_dev(d), dim_x, dim_y, 1.0, 1.96, parity)
+        assert_bit_equal(to_host(dp), oracle.sor_half_sweep(p.copy(), d, 1.0, 1.96, parity), f"colour {parity}")
+
+
+def test_fact1_sweep_order_on_device(ctx, sor_variant):
+    d = torch.ones(4, 5, dtype=torch.float32, device="cuda")
+    p = torch.full((4, 5), 7.0, dtype=torch.float32, device="cuda")
+    ctx.poisson_solve(p, d, 5, 4, 1.0, 1, 1.0)
+    p = to_host(p)
+    assert p[0, 0] == np.float32(-0.5) and p[1, 1] == np.float32(-0.25)
+    assert abs(p[0, 1] + 0.6944) < 1e-4 and abs(p[1, 2] + 0.5208) < 1e-4
+
+
+def test_apply_drags(ctx, oracle):
+    dim_x, dim_y = 61, 81
+    v, _ = rand_fields(9, dim_x, dim_y, 10.0)
+    dr = rand_drags(10, dim_x, dim_y, 300, oob=True)          # > one parameter chunk, some out of range
+    dr[17] = dr[3]                                            # duplicate node: later record wins
+    dr[17]["vx"] = 123.0
+    dv = to_dev(v)
+    ctx.apply_drags(dv, dr, dim_x, dim_y)
+    assert_bit_equal(to_host(dv), oracle.apply_drags(v.copy(), dr), "drags")
+
+
+@pytest.mark.parametrize("shape", [(2, 2), (5, 4), (61, 81), (33, 100), (200, 67)])
+def test_upscale4_rgb565(ctx, oracle, shape):
+    dim_x, dim_y = shape
+    _, c = rand_fields(11, dim_x, dim_y, 1.0)
+    out = torch.zeros((dim_x - 1) * 4, (dim_y - 1) * 4, dtype=torch.int16, device="cuda")
+    ctx.upscale4_rgb565(out, to_dev(c), dim_x, dim_y)
+    assert_bit_equal(to_host(out, np.uint16), oracle.upscale4_rgb565(c), "rgb565 frame")
+
+
+# ---- whole steps ------------------------------------------------------------------------
+
+def run_steps(ctx, v, c, drags_per_step, iters, want_fields=True):
+    dim_y, dim_x = v.shape[:2]
+    dv, dc = to_dev(v), to_dev(c)
+    dp = torch.empty(dim_y, dim_x, dtype=torch.float32, device="cuda")
+    dd = torch.empty_like(dp)
+    for dr in drags_per_step:
+        ctx.step(dv, dc, dr, dim_x, dim_y, DT, 1.0, iters, 1.96, dp, dd)
+    return to_host(dv), to_host(dc, np.uint32), to_host(dp), to_host(dd)
+
+
+@pytest.mark.parametrize("fuse", [0, 1], ids=["unfused", "fused"])
+@pytest.mark.parametrize("shape,iters,steps", [((61, 81), 10, 100), ((80, 60), 10, 20), ((7, 3), 10, 5),
+                                               ((2, 2), 3, 3), ((300, 260), 50, 3), ((1024, 1024), 50, 2)])
+def test_step_matches_oracle(ctx, oracle, shape, iters, steps, fuse):
+    """north_star: <=1e-5/step and bounded drift over 100 steps; measured drift here is 0 bits."""
+    from esp32_fluid_simulation_b200 import synth
+    ctx.set_option("fuse", fuse)
+    try:
+        dim_x, dim_y = shape
+        v = synth.velocity(dim_x, dim_y, vmax=60.0)
+        c = synth.dye(dim_x, dim_y)
+        drs = [synth.drags(dim_x, dim_y, s, n=16) for s in range(steps)]
+        got = run_steps(ctx, v, c, drs, iters)
+        ov, oc = v.copy(), c.copy()
+        for dr in drs:
+            ov, oc, op, od = oracle.step(ov, oc, dr, DT, 1.0, iters, 1.96, want_fields=True)
+        for name, g, w in zip("vcpd", got, (ov, oc, op, od)):
+            assert_bit_equal(g, w, f"{name} after {steps} steps")
+    finally:
+        ctx.set_option("fuse", 1)
+
+
+def test_step_golden_regression(ctx, golden):
+    """The committed 20-step fixture generated from the reference itself."""
+    g = golden("regress20_61x81.npz")
+    got = run_steps(ctx, g["v0"], g["c0"], [None] * 20, 10)
+    for name, a in zip("vcpd", got):
+        assert_bit_equal(a, g[name], name)
+
+
+def test_step_golden_with_drags(ctx, golden):
+    g = golden("steps_drags.npz")
+    for k in ("33x17", "80x60"):
+        got = run_steps(ctx, g[k + "_v0"], g[k + "_c0"], [g[k + "_drags"]] * 5, 10)
+        for name, a in zip("vcpd", got):
+            assert_bit_equal(a, g[k + "_" + name], f"{k} {name}")
+
+
+def test_host_pointer_dropins(ctx, oracle):
+    """fsh_*: numpy in, numpy out — the literal drop-in for a reference call."""
+    import esp32_fluid_simulation_b200 as fb
+    dim_x, dim_y = 61, 81
+    v, c = rand_fields(12, dim_x, dim_y, 70.0)
+    out = np.empty_like(v)
+    fb.advect(out, v, v, dim_x, dim_y, DT, True, ctx=ctx)
+    assert_bit_equal(out, oracle.advect_vec2f(v, v, DT, 1), "fsh advect v")
+    outc = np.empty_like(c)
+    fb.advect(outc, c, v, dim_x, dim_y, DT, False, ctx=ctx)
+    assert_bit_equal(outc, oracle.advect_rgb_uq32(c, v, DT, 0), "fsh advect dye")
+    div = np.empty((dim_y, dim_x), np.float32)
+    fb.calculate_divergence(div, v, dim_x, dim_y, 1.0, ctx=ctx)
+    assert_bit_equal(div, oracle.calculate_divergence(v, 1.0), "fsh div")
+    p = np.empty_like(div)
+    fb.poisson_solve(p, div, dim_x, dim_y, 1.0, 10, 1.96, ctx=ctx)
+    assert_bit_equal(p, oracle.poisson_solve(div, 1.0, 10, 1.96), "fsh poisson")
+    v2 = v.copy()
+    fb.subtract_gradient(v2, p, dim_x, dim_y, 1.0, ctx=ctx)
+    assert_bit_equal(v2, oracle.subtract_gradient(v.copy(), p, 1.0), "fsh grad")
+    dr = rand_drags(13, dim_x, dim_y, 5)
+    hv, hc = v.copy(), c.copy()
+    hp, hd = np.empty_like(div), np.empty_like(div)
+    ctx.step(hv, hc, dr, dim_x, dim_y, DT, 1.0, 10, 1.96, hp, hd)
+    ov, oc, op, od = oracle.step(v.copy(), c.copy(), dr, DT, 1.0, 10, 1.96, want_fields=True)
+    for name, a, b in zip("vcpd", (hv, hc, hp, hd), (ov, oc, op, od)):
+        assert_bit_equal(a, b, f"fsh step {name}")
+    img = np.empty(((dim_x - 1) * 4, (dim_y - 1) * 4), np.uint16)
+    ctx.upscale4_rgb565(img, c, dim_x, dim_y)
+    assert_bit_equal(img, oracle.upscale4_rgb565(c), "fsh upscale")
+
+
+def test_invalid_arguments(ctx):
+    import esp32_fluid_simulation_b200 as fb
+    v = torch.zeros(4, 4, 2, device="cuda")
+    with pytest.raises(fb.FluidError):
+        ctx.advect(v, v, v, 4, 4, DT, True)                  # next_p aliases p
+    with pytest.raises(fb.FluidError):
+        ctx.calculate_divergence(torch.zeros(4, 1, device="cuda"), torch.zeros(4, 1, 2, device="cuda"), 1, 4, 1.0)
+    p = torch.zeros(4, 4, device="cuda")
+    with pytest.raises(fb.FluidError):
+        ctx.poisson_solve(p, p, 4, 4, 1.0, 1, 1.0)           # p aliases div
+    with pytest.raises(ValueError):
+        ctx.poisson_solve(p, np.zeros((4, 4), np.float32), 4, 4, 1.0, 1, 1.0)
+
+
+# ---- BASELINE.json full sizes: oracle where it finishes in seconds, properties beyond ------
+
+def test_4096_one_step_vs_oracle(ctx, oracle):
+    """configs[2]: 4096x4096, 50 SOR iterations — one full step against the oracle (~6 s of CPU)."""
+    from esp32_fluid_simulation_b200 import synth
+    n = 4096
+    v, c = synth.velocity(n, n), synth.dye(n, n)
+    dr = synth.drags(n, n, 0, n=16)
+    got = run_steps(ctx, v, c, [dr], 50)
+    ov, oc, op, od = oracle.step(v, c, dr, DT, 1.0, 50, 1.96, want_fields=True)
+    for name, a, b in zip("vcpd", got, (ov, oc, op, od)):
+        assert_bit_equal(a, b, f"4096^2 {name}")
+
+
+def test_4096_size_independent_properties(ctx):
+    """(a) SOR is linear in d and power-of-two scaling is exact in binary floating point, so
+    solve(4*d) == 4*solve(d) bit for bit; (b) the initial contents of p are ignored; (c) zero
+    velocity makes velocity advection the identity and rounds the dye to 24 significant bits."""
+    n = 4096
+    g = torch.Generator(device="cuda").manual_seed(1)
+    d = torch.randn(n, n, device="cuda", generator=g) * 10
+    p1 = torch.full((n, n), 3.0, device="cuda")
+    p2 = torch.full((n, n), -9.0, device="cuda")
+    ctx.poisson_solve(p1, d, n, n, 1.0, 50, 1.96)
+    ctx.poisson_solve(p2, d * 4, n, n, 1.0, 50, 1.96)
+    assert torch.equal(p1 * 4, p2)
+    v = torch.randn(n, n, 2, device="cuda", generator=g)
+    z = torch.zeros_like(v)
+    out = torch.empty_like(v)
+    ctx.advect(out, v, z, n, n, DT, True)
+    assert torch.equal(out, v)
+    c = torch.randint(2 ** 24, 2 ** 30, (n, n, 3), device="cuda", dtype=torch.int32, generator=g)
+    outc = torch.empty_like(c)
+    ctx.advect(outc, c, z, n, n, DT, False)
+    want = c.to(torch.float32).to(torch.int64).clamp(max=2 ** 31 - 1).to(torch.int32)  # RNE to 24 bits
+    want[-1, -1] = c[-1, -1]                                  # corner-copy node is exact
+    assert torch.equal(outc, want)
