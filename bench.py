@@ -211,6 +211,7 @@ def bench_single(args, fb, synth, torch):
         for s in range(args.warmup, args.warmup + args.steps):
             step(s)
         ev1.record(stream)
+        launches = ctx.launch_count - launches0
         stream.synchronize()
         torch.cuda.synchronize()
         # keep the device busy a little longer so the sampler sees clocks under load
@@ -218,7 +219,6 @@ def bench_single(args, fb, synth, torch):
         while time.time() < t_end:
             step(args.warmup)
         stream.synchronize()
-    launches = ctx.launch_count - launches0
     ms = ev0.elapsed_time(ev1) / args.steps
     value = nodes / (ms * 1e-3) / 1e6
 

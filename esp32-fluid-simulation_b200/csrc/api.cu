@@ -209,7 +209,7 @@ int fs_ctx_create(fs_ctx **out, int device, void *stream)
     ctx->stream = (cudaStream_t)stream;
     ctx->num_sms = prop.multiProcessorCount;
     ctx->opt_sor = 1;
-    ctx->opt_sor_t = 4;
+    ctx->opt_sor_t = 8;
     ctx->opt_sor_shape = 0;
     ctx->opt_advect = 1;
     ctx->opt_fuse = 1;

@@ -1,0 +1,387 @@
+"""2-D block decomposition of one big grid over the GPUs of a node.
+
+One process per GPU (torch.distributed).  Rank r owns a rectangle of the global
+grid and holds a padded local WINDOW of every field: its rectangle plus `ghost`
+nodes towards every neighbouring rank (none towards a domain wall).  All sim
+kernels run through the window ("tile") entry points of the C ABI, which
+evaluate wall rules, red/black parity and advect coordinates in GLOBAL
+coordinates — so a decomposed run is bit-identical to the single-GPU run (and to
+the reference).
+
+Exchanges per step (each one batched send/recv to <= 8 neighbours, corners
+included, over NCCL on NVLink):
+  1. forced velocity, width H+1, so the divergence can be formed on the rectangle
+     grown by H (H = half-sweeps fused per SOR pass);
+  2. pressure, width H, after every SOR pass but the last; width 1 after the last;
+  3. projected velocity + dye, width = this step's max displacement, before the dye
+     advect.  The same velocity halo serves the NEXT step's velocity advect.
+One scalar all-reduce(max) per step sizes exchange 3.
+
+The host logic here is backend-agnostic: `CudaTileOps` drives the CUDA library,
+tests drive the same `DecomposedSim` with a CPU backend over gloo.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+# ---------------------------------------------------------------------------------------
+# geometry (pure python; no torch)
+# ---------------------------------------------------------------------------------------
+
+
+def process_grid(world: int) -> tuple[int, int]:
+    """(Px, Py): ranks along dim_x (fast axis) and dim_y.  1->1x1, 2->1x2, 4->2x2, 8->2x4."""
+    px = 1
+    while (px * 2) * (px * 2) <= world and world % (px * 2) == 0:
+        px *= 2
+    return px, world // px
+
+
+def split(n: int, parts: int, k: int, align: int = 4) -> tuple[int, int]:
+    """[lo, hi) of part k when n nodes are cut into `parts` nearly equal pieces whose
+    boundaries are multiples of `align` (keeps window rows 16-byte aligned)."""
+    def cut(i):
+        if i <= 0:
+            return 0
+        if i >= parts:
+            return n
+        c = (n * i) // parts
+        return (c // align) * align
+    return cut(k), cut(k + 1)
+
+
+@dataclass
+class Window:
+    """One rank's window; mirrors fs_tile."""
+    gdim_x: int
+    gdim_y: int
+    ox: int
+    oy: int
+    nx: int
+    ny: int
+    x0: int
+    y0: int
+    x1: int
+    y1: int
+
+    def rect(self, grow: int = 0) -> "Window":
+        """Same window, compute rectangle grown by `grow` (clipped to the window)."""
+        return Window(self.gdim_x, self.gdim_y, self.ox, self.oy, self.nx, self.ny,
+                      max(self.x0 - grow, 0), max(self.y0 - grow, 0),
+                      min(self.x1 + grow, self.nx), min(self.y1 + grow, self.ny))
+
+
+class Decomposition:
+    def __init__(self, gdim_x: int, gdim_y: int, world: int, rank: int, ghost: int = 64,
+                 grid: tuple[int, int] | None = None):
+        self.px, self.py = grid or process_grid(world)
+        assert self.px * self.py == world, (self.px, self.py, world)
+        self.world, self.rank, self.ghost = world, rank, ghost
+        self.gdim_x, self.gdim_y = gdim_x, gdim_y
+        self.rx, self.ry = rank % self.px, rank // self.px
+        self.gx0, self.gx1 = split(gdim_x, self.px, self.rx)
+        self.gy0, self.gy1 = split(gdim_y, self.py, self.ry)
+        gl = ghost if self.rx > 0 else 0
+        gr = ghost if self.rx < self.px - 1 else 0
+        gd = ghost if self.ry > 0 else 0
+        gu = ghost if self.ry < self.py - 1 else 0
+        self.window = Window(gdim_x, gdim_y, self.gx0 - gl, self.gy0 - gd,
+                             (self.gx1 - self.gx0) + gl + gr, (self.gy1 - self.gy0) + gd + gu,
+                             gl, gd, gl + (self.gx1 - self.gx0), gd + (self.gy1 - self.gy0))
+        w = self.window
+        assert w.ox >= 0 and w.oy >= 0 and w.ox + w.nx <= gdim_x and w.oy + w.ny <= gdim_y, \
+            "ghost wider than the neighbouring rank's rectangle"
+
+    def rank_of(self, rx: int, ry: int) -> int | None:
+        if 0 <= rx < self.px and 0 <= ry < self.py:
+            return ry * self.px + rx
+        return None
+
+    def neighbours(self):
+        """[(peer_rank, dx, dy)] for the up-to-8 surrounding ranks, in an order that is the
+        mirror image on the peer (so batched send/recv pairs line up)."""
+        out = []
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                if dx == 0 and dy == 0:
+                    continue
+                peer = self.rank_of(self.rx + dx, self.ry + dy)
+                if peer is not None:
+                    out.append((peer, dx, dy))
+        return out
+
+    def send_slices(self, dx: int, dy: int, width: int):
+        """Slices (rows, cols) of the window that neighbour (dx,dy) needs: the strip of MY
+        rectangle adjacent to it, `width` deep."""
+        w = self.window
+        xs = {-1: slice(w.x0, w.x0 + width), 0: slice(w.x0, w.x1), 1: slice(w.x1 - width, w.x1)}[dx]
+        ys = {-1: slice(w.y0, w.y0 + width), 0: slice(w.y0, w.y1), 1: slice(w.y1 - width, w.y1)}[dy]
+        return ys, xs
+
+    def recv_slices(self, dx: int, dy: int, width: int):
+        """Slices of MY ghost region filled by neighbour (dx,dy)."""
+        w = self.window
+        xs = {-1: slice(w.x0 - width, w.x0), 0: slice(w.x0, w.x1), 1: slice(w.x1, w.x1 + width)}[dx]
+        ys = {-1: slice(w.y0 - width, w.y0), 0: slice(w.y0, w.y1), 1: slice(w.y1, w.y1 + width)}[dy]
+        return ys, xs
+
+
+# ---------------------------------------------------------------------------------------
+# the decomposed step
+# ---------------------------------------------------------------------------------------
+
+class DecomposedSim:
+    """State windows + step sequencing for one rank.
+
+    `ops` is the compute backend (tile_* methods with the signatures of
+    ops.Context; + `empty(shape, dtype)`, `max_displacement`).  `comm` wraps
+    torch.distributed (isend/irecv batch + all-reduce max).
+    """
+
+    def __init__(self, dec: Decomposition, ops, comm, iters: int, sor_t: int,
+                 dt=np.float32(1 / 30.0), dx=np.float32(1.0), omega=np.float32(1.96)):
+        self.dec, self.ops, self.comm = dec, ops, comm
+        self.iters, self.sor_t = iters, max(1, sor_t)
+        self.dt, self.dx, self.omega = dt, dx, omega
+        w = dec.window
+        need = 2 * min(self.sor_t, max(iters, 1)) + 1
+        if dec.world > 1 and dec.ghost < need:
+            raise ValueError(f"ghost={dec.ghost} is narrower than the {need} nodes one SOR pass needs")
+        self.v = ops.empty((w.ny, w.nx, 2), "float32")
+        self.v2 = ops.empty((w.ny, w.nx, 2), "float32")
+        self.c = ops.empty((w.ny, w.nx, 3), "uint32")
+        self.c2 = ops.empty((w.ny, w.nx, 3), "uint32")
+        self.div = ops.empty((w.ny, w.nx), "float32")
+        self.p = ops.empty((w.ny, w.nx), "float32")
+        self.p2 = ops.empty((w.ny, w.nx), "float32")
+        self.v_halo = 0          # ghost width of self.v that is currently valid
+        self.need_halo = None    # halo the next advect needs (nodes), None = unknown
+        self.exchanges = 0
+
+    # -- state --------------------------------------------------------------------------
+    def load(self, v_window: np.ndarray, c_window: np.ndarray):
+        """Fill the windows (rectangle + whatever ghosts the caller has; ghosts are refreshed
+        by exchange before they are read)."""
+        self.ops.upload(self.v, v_window)
+        self.ops.upload(self.c, c_window)
+        self.v_halo = 0
+        self.need_halo = None
+
+    def owned(self, field) -> np.ndarray:
+        w = self.dec.window
+        return self.ops.download(field)[w.y0:w.y1, w.x0:w.x1]
+
+    # -- communication ------------------------------------------------------------------
+    def exchange(self, fields, width: int):
+        """Refresh `width` ghost nodes of every field in `fields` from the 8 neighbours."""
+        if self.dec.world == 1 or width <= 0:
+            return
+        if width > self.dec.ghost:
+            raise RuntimeError(
+                f"halo of {width} nodes needed but windows carry ghost={self.dec.ghost}; "
+                "re-create the simulation with a larger ghost")
+        sends, recvs = [], []
+        for peer, dx, dy in self.dec.neighbours():
+            for f in fields:
+                ys, xs = self.dec.send_slices(dx, dy, width)
+                sends.append((peer, f[ys, xs]))
+                ys, xs = self.dec.recv_slices(dx, dy, width)
+                recvs.append((peer, f, ys, xs))
+        self.comm.exchange(sends, recvs)
+        self.exchanges += 1
+
+    def _agree_halo(self, vel) -> int:
+        local = self.ops.max_displacement(vel, self.dec.window, self.dt)
+        return self.comm.all_max(local)
+
+    # -- one loop() body (ino:249-289) ------------------------------------------------------
+    def step(self, drags):
+        ops, w = self.ops, self.dec.window
+        T, iters = self.sor_t, self.iters
+        # advect velocity (ino:253): needs v valid `need_halo` nodes around the rectangle
+        if self.need_halo is None:
+            self.need_halo = self._agree_halo(self.v)
+        if self.v_halo < self.need_halo:
+            self.exchange([self.v], self.need_halo)
+            self.v_halo = self.need_halo
+        ops.tile_advect(self.v2, self.v, self.v, w, self.dt, True)
+        ops.tile_check()
+        # drags (ino:264-269): every rank applies the records that land in its rectangle
+        if drags is not None and len(drags):
+            ops.tile_apply_drags(self.v2, drags, w)
+        # divergence on the rectangle grown by H so each SOR pass can recompute its halo
+        passes = [min(T, iters - k) for k in range(0, iters, T)] if iters > 0 else []
+        H0 = 2 * passes[0] if passes else 0
+        self.exchange([self.v2], H0 + 1)
+        ops.tile_calculate_divergence(self.div, self.v2, w.rect(H0), self.dx)          # ino:274
+        # SOR (ino:275): p starts at zero; ping-pong p/p2, exchange H ghosts between passes
+        src, dst = None, self.p
+        if not passes:
+            ops.zero(self.p)
+        for k, t in enumerate(passes):
+            ops.tile_sor_sweeps(dst, src, self.div, w, self.dx, self.omega, 0, 2 * t)
+            nxt = 2 * passes[k + 1] if k + 1 < len(passes) else 1
+            self.exchange([dst], nxt)
+            src, dst = dst, (self.p2 if dst is self.p else self.p)
+        p_final = src if src is not None else self.p
+        ops.tile_subtract_gradient(self.v2, p_final, w, self.dx)                       # ino:276
+        self.p_last = p_final
+        # dye advect (ino:282) with the projected velocity; its halo also serves the next step
+        h = self._agree_halo(self.v2)
+        self.exchange([self.v2, self.c], h)
+        ops.tile_advect(self.c2, self.c, self.v2, w, self.dt, False)
+        ops.tile_check()
+        self.v, self.v2 = self.v2, self.v
+        self.c, self.c2 = self.c2, self.c
+        self.v_halo, self.need_halo = h, h
+
+
+# ---------------------------------------------------------------------------------------
+# torch.distributed plumbing (NCCL on GPUs, gloo in the CPU tests)
+# ---------------------------------------------------------------------------------------
+
+class TorchComm:
+    def __init__(self, device):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.device = torch, dist, device
+
+    def exchange(self, sends, recvs):
+        torch, dist = self.torch, self.dist
+        ops, landing = [], []
+        for peer, view in sends:
+            ops.append(dist.P2POp(dist.isend, view.contiguous(), peer))
+        for peer, field, ys, xs in recvs:
+            buf = torch.empty_like(field[ys, xs])
+            ops.append(dist.P2POp(dist.irecv, buf, peer))
+            landing.append((field, ys, xs, buf))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for field, ys, xs, buf in landing:
+            field[ys, xs] = buf
+
+    def all_max(self, value: int) -> int:
+        t = self.torch.tensor([int(value)], dtype=self.torch.int32, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return int(t.item())
+
+
+class CudaTileOps:
+    """Backend of DecomposedSim over the CUDA library (tile entry points of the C ABI).
+    The context runs on torch's CURRENT stream so NCCL ops order with the kernels."""
+
+    def __init__(self, device: int):
+        import torch
+
+        from . import ops as _ops
+        from ._lib import Tile
+        self.torch, self.Tile = torch, Tile
+        self.device = torch.device("cuda", device)
+        self.ctx = _ops.Context(device, torch.cuda.current_stream(self.device))
+
+    def _tile(self, w: Window):
+        return self.Tile(w.gdim_x, w.gdim_y, w.ox, w.oy, w.nx, w.ny, w.x0, w.y0, w.x1, w.y1)
+
+    def empty(self, shape, dtype):
+        tdt = {"float32": self.torch.float32, "uint32": self.torch.int32}[dtype]
+        return self.torch.zeros(shape, dtype=tdt, device=self.device)
+
+    def zero(self, t):
+        t.zero_()
+
+    def upload(self, dst, a: np.ndarray):
+        if a.dtype == np.uint32:
+            a = a.view(np.int32)
+        dst.copy_(self.torch.from_numpy(np.ascontiguousarray(a)))
+
+    def download(self, t) -> np.ndarray:
+        a = t.cpu().numpy()
+        return a.view(np.uint32) if a.dtype == np.int32 else a
+
+    def tile_advect(self, next_p, p, vel, w, dt, no_slip):
+        self.ctx.tile_advect(next_p, p, vel, self._tile(w), dt, no_slip)
+
+    def tile_check(self):
+        pass  # the halo is sized from an agreed max displacement; an overrun cannot happen
+
+    def tile_apply_drags(self, v, drags, w):
+        self.ctx.tile_apply_drags(v, drags, self._tile(w))
+
+    def tile_calculate_divergence(self, div, v, w, dx):
+        self.ctx.tile_calculate_divergence(div, v, self._tile(w), dx)
+
+    def tile_subtract_gradient(self, v, p, w, dx):
+        self.ctx.tile_subtract_gradient(v, p, self._tile(w), dx)
+
+    def tile_sor_sweeps(self, p_out, p_in, div, w, dx, omega, first_parity, n_half):
+        self.ctx.tile_sor_sweeps(p_out, p_in, div, self._tile(w), dx, omega, first_parity, n_half)
+
+    def max_displacement(self, vel, w, dt) -> int:
+        return self.ctx.tile_max_displacement(vel, self._tile(w), dt)
+
+
+# ---------------------------------------------------------------------------------------
+# bench.py's N>1 leg
+# ---------------------------------------------------------------------------------------
+
+def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
+    """Weak scaling: every GPU owns tile_edge x tile_edge nodes of one global grid."""
+    import os
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    from . import synth
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    px, py = process_grid(world)
+    gx, gy = tile_edge * px, tile_edge * py
+    dev = torch.device("cuda", local_rank)
+    ops = CudaTileOps(local_rank)
+    sor_t = ops.ctx.get_option("sor_t")
+    dec = Decomposition(gx, gy, world, rank, ghost=64)
+    sim = DecomposedSim(dec, ops, TorchComm(dev), iters, sor_t, synth.DT, synth.DX, synth.OMEGA)
+    w = dec.window
+    sim.load(synth.velocity(gx, gy, window=(w.ox, w.oy, w.nx, w.ny)),
+             synth.dye(gx, gy, window=(w.ox, w.oy, w.nx, w.ny)))
+    drags = [synth.drags(gx, gy, s, n=n_drags) for s in range(args.warmup + args.steps)]
+    for s in range(args.warmup):
+        sim.step(drags[s])
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    launches0, ex0 = ops.ctx.launch_count, sim.exchanges
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for s in range(args.warmup, args.warmup + args.steps):
+        sim.step(drags[s])
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e0.elapsed_time(e1), wall_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0].item()) / args.steps
+    nodes = gx * gy
+    value = nodes / (ms * 1e-3) / 1e6
+    return {
+        "metric": "Mcell-steps/s (advect+project, 50 SOR iters) at 4096^2", "value": value,
+        "unit": "Mcell-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32+uq32", "data": "synthetic",
+        "config": {"workload": f"{gx}x{gy} grid block-decomposed {px}x{py}, {tile_edge}x{tile_edge} nodes per GPU, "
+                               f"{iters} SOR iterations, velocity + dye advection",
+                   "grid": [gx, gy], "process_grid": [px, py], "ghost": dec.ghost, "sor_t": sor_t,
+                   "halo_exchanges_per_step": (sim.exchanges - ex0) / args.steps,
+                   "l2": "per-GPU state exceeds the 126 MB L2; no flush needed",
+                   "timing": "CUDA events on the compute stream, max over ranks"},
+        "wall_ms_per_step_max": float(t[1].item()) / args.steps,
+        "gpu_launches": int(ops.ctx.launch_count - launches0),
+        "e2e": None, "roofline": None, "cpu_baseline": None,
+    }

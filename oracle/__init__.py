@@ -57,6 +57,12 @@ def _dims(a):
     return int(a.shape[1]), int(a.shape[0])  # dim_x (fast), dim_y (slow)
 
 
+class OracleTile(C.Structure):
+    """oracle_tile — same fields as fs_tile (include/fluid_b200.h)."""
+    _fields_ = [(n, C.c_int) for n in
+                ("gdim_x", "gdim_y", "ox", "oy", "nx", "ny", "x0", "y0", "x1", "y1")]
+
+
 class _Base:
     prefix = ""
     path = ""
@@ -176,6 +182,55 @@ class Oracle(_Base):
         L.oracle_init_color_wheel.restype = None
         L.oracle_fnv1a64.argtypes = [C.c_void_p, C.c_uint64]
         L.oracle_fnv1a64.restype = C.c_uint64
+
+    # --- window ("tile") operators, used as the CPU backend of the decomposed path's tests ---
+    def _tile_sigs(self):
+        if getattr(self, "_tiles_bound", False):
+            return
+        L = self.lib
+        F, U, I, f = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.c_int, C.c_float
+        T = C.POINTER(OracleTile)
+        L.oracle_tile_advect_vec2f.argtypes = [F, F, F, T, f, I]
+        L.oracle_tile_advect_vec2f.restype = I
+        L.oracle_tile_advect_rgb_uq32.argtypes = [U, U, F, T, f, I]
+        L.oracle_tile_advect_rgb_uq32.restype = I
+        L.oracle_tile_calculate_divergence.argtypes = [F, F, T, f]
+        L.oracle_tile_subtract_gradient.argtypes = [F, F, T, f]
+        L.oracle_tile_sor_sweeps.argtypes = [F, F, F, T, f, f, I, I]
+        L.oracle_tile_apply_drags.argtypes = [F, C.c_void_p, I, T]
+        for n in ("calculate_divergence", "subtract_gradient", "sor_sweeps", "apply_drags"):
+            getattr(L, "oracle_tile_" + n).restype = None
+        self._tiles_bound = True
+
+    @staticmethod
+    def _t(tile):
+        return OracleTile(*[getattr(tile, n) for n, _ in OracleTile._fields_])
+
+    def tile_advect(self, next_p, p, vel, tile, dt, no_slip):
+        """Returns True if a backtrace left the window (FS_ERR_HALO_OVERRUN in the product)."""
+        self._tile_sigs()
+        t = self._t(tile)
+        if p.dtype == np.float32:
+            return bool(self.lib.oracle_tile_advect_vec2f(_f32(next_p), _f32(p), _f32(vel), C.byref(t), dt, int(no_slip)))
+        return bool(self.lib.oracle_tile_advect_rgb_uq32(_u32(next_p), _u32(p), _f32(vel), C.byref(t), dt, int(no_slip)))
+
+    def tile_calculate_divergence(self, div, v, tile, dx):
+        self._tile_sigs()
+        self.lib.oracle_tile_calculate_divergence(_f32(div), _f32(v), C.byref(self._t(tile)), dx)
+
+    def tile_subtract_gradient(self, v, p, tile, dx):
+        self._tile_sigs()
+        self.lib.oracle_tile_subtract_gradient(_f32(v), _f32(p), C.byref(self._t(tile)), dx)
+
+    def tile_sor_sweeps(self, p_out, p_in, div, tile, dx, omega, first_parity, n_half):
+        self._tile_sigs()
+        self.lib.oracle_tile_sor_sweeps(_f32(p_out), _f32(p_in) if p_in is not None else None, _f32(div),
+                                        C.byref(self._t(tile)), dx, omega, first_parity, n_half)
+
+    def tile_apply_drags(self, v, drags, tile):
+        self._tile_sigs()
+        drags = np.ascontiguousarray(drags, DRAG_DTYPE)
+        self.lib.oracle_tile_apply_drags(_f32(v), drags.ctypes.data, len(drags), C.byref(self._t(tile)))
 
     def sor_half_sweep(self, p, div, dx, omega, parity):
         dx_, dy_ = _dims(p)

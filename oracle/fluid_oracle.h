@@ -25,6 +25,10 @@ typedef struct {            /* struct drag, ino:45-48 */
     float vx, vy;           /* velocity.x, velocity.y (graphics frame) */
 } oracle_drag;
 
+typedef struct {            /* same fields as fs_tile (include/fluid_b200.h) */
+    int gdim_x, gdim_y, ox, oy, nx, ny, x0, y0, x1, y1;
+} oracle_tile;
+
 uint32_t oracle_uq32_from_float(float x);   /* uq32.h:13, saturating */
 float oracle_uq32_to_float(uint32_t raw);   /* uq32.h:15 */
 
@@ -54,6 +58,19 @@ void oracle_upscale4_rgb565(uint16_t *out, const uint32_t *c, int dim_x,
                             int dim_y);                        /* ino:116-177 */
 void oracle_init_color_wheel(float *v, uint32_t *c, int dim_x, int dim_y);
                                                                /* ino:196-241 */
+/* the same operators over a window of a global grid (for the decomposed path);
+ * the whole-grid functions above are the ox=oy=0 special case of these */
+int oracle_tile_advect_vec2f(float *next_p, const float *p, const float *vel,
+                             const oracle_tile *t, float dt, int no_slip);
+int oracle_tile_advect_rgb_uq32(uint32_t *next_c, const uint32_t *c, const float *vel,
+                                const oracle_tile *t, float dt, int no_slip);
+void oracle_tile_calculate_divergence(float *div, const float *v, const oracle_tile *t, float dx);
+void oracle_tile_subtract_gradient(float *v, const float *p, const oracle_tile *t, float dx);
+void oracle_tile_sor_sweeps(float *p_out, const float *p_in, const float *div,
+                            const oracle_tile *t, float dx, float omega, int first_parity,
+                            int n_half);
+void oracle_tile_apply_drags(float *v, const oracle_drag *drags, int n, const oracle_tile *t);
+
 uint64_t oracle_fnv1a64(const void *data, uint64_t nbytes);
 
 #ifdef __cplusplus

@@ -106,7 +106,7 @@ def test_poisson_solve_every_blocking_depth(ctx, oracle, t_block):
             ctx.poisson_solve(p, to_dev(d), dim_x, dim_y, 1.0, iters, 1.96)
             assert_bit_equal(to_host(p), oracle.poisson_solve(d, 1.0, iters, 1.96), f"T={t_block}")
     finally:
-        ctx.set_option("sor_t", 4)
+        ctx.set_option("sor_t", 8)
 
 
 def test_half_sweep_colours(ctx, oracle):
