@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--out", default="")
+    ap.add_argument("--ensemble", type=int, default=0, help="batch size: bench the smem-resident ensemble kernel instead")
+    ap.add_argument("--ens-shape", default="80x60")
     args = ap.parse_args()
     nx, ny = args.n, args.ny or args.n
     nodes = nx * ny
@@ -46,6 +48,8 @@ def main():
         pass
     stream = torch.cuda.Stream()
     ctx = fb.Context(0, stream)
+    if args.ensemble:
+        return bench_ensemble(args, ctx, stream, peak)
     with torch.cuda.stream(stream):
         v = torch.from_numpy(synth.velocity(nx, ny)).cuda()
         c = torch.from_numpy(synth.dye(nx, ny).view(np.int32)).cuda()
@@ -105,6 +109,32 @@ def main():
         run_step()
     if args.out:
         json.dump({"grid": [nx, ny], "iters": args.iters, "peak_gbs": peak, "rows": rows}, open(args.out, "w"), indent=1)
+
+
+def bench_ensemble(args, ctx, stream, peak):
+    """BASELINE.json configs[1]: `batch` independent CYD-sized grids, K=10, one CTA per grid."""
+    dim_x, dim_y = (int(x) for x in args.ens_shape.split("x"))
+    batch, iters = args.ensemble, 10
+    n = dim_x * dim_y
+    with torch.cuda.stream(stream):
+        g = torch.Generator(device="cuda").manual_seed(7)
+        v = (torch.rand(batch, dim_y, dim_x, 2, device="cuda", generator=g) - 0.5) * 120.0
+        c = torch.randint(0, 2 ** 31 - 1, (batch, dim_y, dim_x, 3), device="cuda", dtype=torch.int32, generator=g)
+    stream.synchronize()
+    rows = []
+    for n_steps in (1, 4, 16):
+        ms = timeit(stream, lambda: ctx.ensemble_step(v, c, batch, dim_x, dim_y, synth.DT, 1.0, iters, 1.96, n_steps),
+                    reps=3, warm=1)
+        cells = batch * n * n_steps
+        r = {"kernel": f"ensemble_step[{dim_x}x{dim_y} x{batch}, K={iters}, n_steps={n_steps}]", "ms": round(ms, 3),
+             "mcell_steps_per_s": round(cells / (ms * 1e-3) / 1e6, 1),
+             "grid_steps_per_s": round(batch * n_steps / (ms * 1e-3), 1),
+             "hbm_GBps_state_io": round(batch * n * 40 / (ms * 1e-3) / 1e9, 1),
+             "smem_bytes_per_cta": 40 * n}
+        rows.append(r)
+        print(json.dumps(r), flush=True)
+    if args.out:
+        json.dump({"rows": rows}, open(args.out, "w"), indent=1)
 
 
 if __name__ == "__main__":

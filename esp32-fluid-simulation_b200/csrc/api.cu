@@ -9,7 +9,7 @@
 
 using namespace fs;
 
-enum Scratch { S_VTMP = 0, S_CTMP, S_DIV, S_P, S_P2, S_HV, S_HV2, S_HC, S_HC2, S_HP, S_HD, S_HIMG, S_COUNT };
+enum Scratch { S_VTMP = 0, S_CTMP, S_DIV, S_P, S_P2, S_HV, S_HV2, S_HC, S_HC2, S_HP, S_HD, S_HIMG, S_EDRAG, S_ECNT, S_COUNT };
 
 struct fs_ctx {
     int device;
@@ -20,6 +20,7 @@ struct fs_ctx {
     size_t scratch_bytes[S_COUNT];
     int *status_dev;            // device flag raised by tile advects (FS_ERR_HALO_OVERRUN)
     unsigned int *maxdisp_dev;  // max-displacement reduction cell
+    size_t max_smem_optin;
     int opt_sor, opt_sor_t, opt_sor_shape, opt_advect, opt_fuse;
 };
 
@@ -208,6 +209,7 @@ int fs_ctx_create(fs_ctx **out, int device, void *stream)
     ctx->device = device;
     ctx->stream = (cudaStream_t)stream;
     ctx->num_sms = prop.multiProcessorCount;
+    ctx->max_smem_optin = prop.sharedMemPerBlockOptin;
     ctx->opt_sor = 1;
     ctx->opt_sor_t = 8;
     ctx->opt_sor_shape = 0;
@@ -387,11 +389,31 @@ int fs_upscale4_rgb565(uint16_t *out, const fs_rgb_uq32 *c, int dim_x, int dim_y
     return launch_upscale4_rgb565(mk(ctx), out, (const uint32_t *)c, dim_x, dim_y);
 }
 
-int fs_ensemble_step(fs_vec2f *, fs_rgb_uq32 *, const fs_drag *, const int *, int, int, int, int,
-                     float, float, int, float, int, fs_ctx *ctx)
+int fs_ensemble_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags, const int *drag_counts,
+                     int max_drags, int batch, int dim_x, int dim_y, float dt, float dx, int iters,
+                     float omega, int n_steps, fs_ctx *ctx)
 {
     if (!ctx) return FS_ERR_NO_CONTEXT;
-    return FS_ERR_UNSUPPORTED;
+    if (!v || !c || batch < 0 || n_steps < 0 || iters < 0 || max_drags < 0 || bad_dims(dim_x, dim_y) ||
+        (max_drags > 0 && (!drags || !drag_counts)))
+        return FS_ERR_INVALID_ARG;
+    if (!ensemble_supported(dim_x, dim_y, ctx->max_smem_optin)) return FS_ERR_UNSUPPORTED;
+    if (batch == 0 || n_steps == 0) return FS_OK;
+    DeviceGuard guard(ctx->device);
+    void *d_drags = nullptr, *d_counts = nullptr;
+    if (max_drags > 0) {
+        const size_t slots = (size_t)n_steps * batch;
+        int e;
+        if ((e = ensure(ctx, S_EDRAG, slots * max_drags * sizeof(fs_drag), &d_drags))) return e;
+        if ((e = ensure(ctx, S_ECNT, slots * sizeof(int), &d_counts))) return e;
+        FS_CUDA_TRY(cudaMemcpyAsync(d_drags, drags, slots * max_drags * sizeof(fs_drag),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+        FS_CUDA_TRY(cudaMemcpyAsync(d_counts, drag_counts, slots * sizeof(int), cudaMemcpyHostToDevice,
+                                    ctx->stream));
+    }
+    return launch_ensemble(mk(ctx), (float2 *)v, (uint32_t *)c, (const fs_drag *)d_drags,
+                           (const int *)d_counts, max_drags, batch, dim_x, dim_y, dt, dx, iters, omega,
+                           n_steps);
 }
 
 // ---- host-pointer drop-ins --------------------------------------------------------

@@ -37,6 +37,13 @@ constexpr int SOR_BLOCKED_MAX_HALF = 16;
 int launch_sor_blocked(const Launch &L, float *p_out, const float *p_in, const float *div, const Geo &g,
                        float dx, float omega, int first_parity, int n_half, int shape);
 
+// ensemble.cu — whole loop() body per grid, resident in shared memory
+size_t ensemble_smem_bytes(int dim_x, int dim_y);
+bool ensemble_supported(int dim_x, int dim_y, size_t max_smem_optin);
+int launch_ensemble(const Launch &L, float2 *v, uint32_t *c, const fs_drag *drags_dev,
+                    const int *counts_dev, int max_drags, int batch, int dim_x, int dim_y, float dt,
+                    float dx, int iters, float omega, int n_steps);
+
 // upscale.cu — ino:116-177
 int launch_upscale4_rgb565(const Launch &L, uint16_t *out, const uint32_t *c, int dim_x, int dim_y);
 

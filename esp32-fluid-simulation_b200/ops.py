@@ -209,7 +209,7 @@ class Context:
         if max_drags > 0:
             d = np.ascontiguousarray(drags, DRAG_DTYPE)
             cnt = np.ascontiguousarray(drag_counts, np.int32)
-            assert d.size == batch * max_drags and cnt.size == batch
+            assert d.size == n_steps * batch * max_drags and cnt.size == n_steps * batch
             dptr, cptr = d.ctypes.data, cnt.ctypes.data
         check(self._L.fs_ensemble_step(a_v, a_c, dptr, cptr, max_drags, batch, dim_x, dim_y, dt, dx,
                                        iters, omega, n_steps, self._h), "fs_ensemble_step")

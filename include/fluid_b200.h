@@ -111,10 +111,12 @@ int fs_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags, int n_drags,
  * of uint16, row pitch (dim_y-1)*4 (image rows run along the sim's fast axis). */
 int fs_upscale4_rgb565(uint16_t *out, const fs_rgb_uq32 *c, int dim_x, int dim_y,
                        fs_ctx *ctx);
-/* `batch` independent grids, each a full loop() body, one CTA per grid with the
- * grid resident in shared memory (BASELINE.json configs[1]).  v, c hold the
- * grids back to back.  drags: host array of batch*max_drags records, drag_counts:
- * host array of `batch` counts (both may be NULL with max_drags = 0). */
+/* `batch` independent grids, `n_steps` consecutive loop() bodies each, one CTA per
+ * grid with the grid resident in shared memory for the whole call (BASELINE.json
+ * configs[1]).  v, c hold the grids back to back.  drags: HOST array laid out
+ * [n_steps][batch][max_drags], drag_counts: HOST array [n_steps][batch] (both may
+ * be NULL with max_drags = 0).  Needs 40*dim_x*dim_y bytes of shared memory:
+ * FS_ERR_UNSUPPORTED beyond ~5,700 nodes (use fs_step per grid there). */
 int fs_ensemble_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags,
                      const int *drag_counts, int max_drags, int batch, int dim_x,
                      int dim_y, float dt, float dx, int iters, float omega,

@@ -282,3 +282,42 @@ def test_4096_size_independent_properties(ctx):
     want = c.to(torch.float32).to(torch.int64).clamp(max=2 ** 31 - 1).to(torch.int32)  # RNE to 24 bits
     want[-1, -1] = c[-1, -1]                                  # corner-copy node is exact
     assert torch.equal(outc, want)
+
+
+# ---- batched ensemble: one CTA per grid, state resident in shared memory ------------------
+
+@pytest.mark.parametrize("shape,iters,batch,n_steps", [((61, 81), 10, 5, 1), ((80, 60), 10, 300, 3), ((60, 80), 7, 4, 2),
+                                                       ((7, 3), 4, 3, 2), ((2, 2), 3, 2, 1), ((64, 90), 10, 2, 1)])
+def test_ensemble_step(ctx, oracle, shape, iters, batch, n_steps):
+    from esp32_fluid_simulation_b200 import synth
+    dim_x, dim_y = shape
+    max_drags = 4
+    v = np.stack([synth.velocity(dim_x, dim_y, seed=100 + b, vmax=90.0) for b in range(batch)])
+    c = np.stack([synth.dye(dim_x, dim_y, seed=200 + b, n_splats=6) for b in range(batch)])
+    drags = np.zeros((n_steps, batch, max_drags), synth.DRAG_DTYPE)
+    counts = np.zeros((n_steps, batch), np.int32)
+    for s in range(n_steps):
+        for b in range(batch):
+            k = (b + s) % (max_drags + 1)
+            counts[s, b] = k
+            drags[s, b, :k] = synth.drags(dim_x, dim_y, s * 1000 + b, n=max_drags, vmax=300.0)[:k]
+    dv, dc = to_dev(v), to_dev(c)
+    ctx.ensemble_step(dv, dc, batch, dim_x, dim_y, DT, 1.0, iters, 1.96, n_steps, drags, counts, max_drags)
+    gv, gc = to_host(dv), to_host(dc, np.uint32)
+    check = range(batch) if batch <= 8 else [0, 1, 147, 148, 149, batch - 1]
+    for b in check:
+        ov, oc = v[b].copy(), c[b].copy()
+        for s in range(n_steps):
+            ov, oc = oracle.step(ov, oc, drags[s, b, :counts[s, b]], DT, 1.0, iters, 1.96)
+        assert_bit_equal(gv[b], ov, f"grid {b} velocity")
+        assert_bit_equal(gc[b], oc, f"grid {b} dye")
+
+
+def test_ensemble_too_large_is_unsupported(ctx):
+    import esp32_fluid_simulation_b200 as fb
+    from esp32_fluid_simulation_b200._lib import FS_ERR_UNSUPPORTED
+    v = torch.zeros(1, 128, 128, 2, device="cuda")
+    c = torch.zeros(1, 128, 128, 3, device="cuda", dtype=torch.int32)
+    with pytest.raises(fb.FluidError) as e:
+        ctx.ensemble_step(v, c, 1, 128, 128, DT, 1.0, 10, 1.96)
+    assert e.value.code == FS_ERR_UNSUPPORTED
