@@ -93,13 +93,13 @@ def main():
         ctx.set_option("sor", 0)
         run_sor("[half-sweeps]")
         ctx.set_option("sor", 1)
-        for shape in (0, 1):
+        for shape in (0, 1, 2, 3):
             ctx.set_option("sor_shape", shape)
             for t in (1, 2, 3, 4, 5, 6, 8):
                 ctx.set_option("sor_t", t)
                 run_sor(f"[blocked shape={shape} T={t}]")
-        ctx.set_option("sor_shape", 0)
-        ctx.set_option("sor_t", 4)
+        ctx.set_option("sor_shape", 3)
+        ctx.set_option("sor_t", 8)
         for fuse in (0, 1):
             ctx.set_option("fuse", fuse)
             run_step(f"[fuse={fuse}]")

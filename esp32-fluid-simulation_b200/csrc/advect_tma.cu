@@ -1,0 +1,233 @@
+// TMA-tiled advection (advect.h:74-85).
+//
+// One CTA produces a 64x32-node output tile.  The source field's tile plus a
+// CFL-bounded halo (HALO nodes each way, +1 for the upper bilinear corner) is
+// staged into shared memory by ONE bulk-tensor copy (cp.async.bulk.tensor.2d,
+// SASS UTMALDG) while the threads read their velocities and form the backtrace;
+// the four corner reads of every node then hit shared memory.  A backtrace that
+// leaves the staged tile (a touch impulse can move a node dozens of cells,
+// SURVEY.md §7 hard part 6) falls back, per fetch, to an L2 gather from global
+// memory — so the result never depends on the halo width.
+//
+// The field is described to the TMA unit as a 2-D tensor of 32-bit words,
+// NC*nx words per row (NC = 2 for velocity, 3 for UQ32 dye): rows must be
+// 16-byte multiples, which holds for the big grids (the small / odd ones take
+// advect_gather).  Out-of-tensor parts of a box are zero-filled by the hardware
+// and are never sampled: `sample` clamps to the domain first.
+//
+// The dye result (12 B per node) is staged in shared memory and written with a
+// bulk-tensor store (UTMASTG) so the 12-byte AoS elements leave the SM as full
+// lines; velocity (8 B) is stored directly, coalesced.
+#include "advect.cuh"
+#include "kernels.h"
+#include "tma.cuh"
+
+namespace fs {
+
+constexpr int AT_TX = 64, AT_TY = 32, AT_HALO = 4, AT_THREADS = 256;
+
+template <class P>
+struct TileShape {
+    static constexpr int ALIGN = P::NC == 2 ? 2 : 4;   // box rows must be 16-byte multiples
+    static constexpr int W = ((AT_TX + 2 * AT_HALO + 1 + ALIGN - 1) / ALIGN) * ALIGN;
+    static constexpr int H = AT_TY + 2 * AT_HALO + 1;
+    static constexpr int ROW_WORDS = W * P::NC;
+    static constexpr int IN_BYTES = ROW_WORDS * H * 4;
+    static constexpr int OUT_BYTES = P::NC == 3 ? AT_TX * AT_TY * 12 : 0;
+    static_assert(ROW_WORDS <= 256, "TMA box dimension limit");
+};
+
+// Fetch a source node: shared-memory tile if staged, else global (L2) gather.
+template <class P>
+struct TileFetch {
+    const typename P::raw_t *tile;   // smem, ROW_WORDS words per row
+    const typename P::raw_t *base;   // global window
+    int bx0, by0;                    // local coordinate of the tile's first staged node
+    int ox, oy, nx, ny;
+    int *status;
+    __device__ __forceinline__ void operator()(int gi, int gj, typename P::raw_t (&o)[P::NC]) const
+    {
+        const int lx = gi - ox, ly = gj - oy;
+        if ((unsigned)lx >= (unsigned)nx || (unsigned)ly >= (unsigned)ny) {  // not in this rank's window
+            if (status) atomicExch(status, FS_ERR_HALO_OVERRUN);
+#pragma unroll
+            for (int ch = 0; ch < P::NC; ch++) o[ch] = 0;
+            return;
+        }
+        const int tx = lx - bx0, ty = ly - by0;
+        if ((unsigned)tx < (unsigned)TileShape<P>::W && (unsigned)ty < (unsigned)TileShape<P>::H) {
+            const typename P::raw_t *q = tile + ty * TileShape<P>::ROW_WORDS + tx * P::NC;
+            if constexpr (P::NC == 2) {
+                const float2 t = *reinterpret_cast<const float2 *>(q);
+                o[0] = t.x;
+                o[1] = t.y;
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < P::NC; ch++) o[ch] = q[ch];
+            }
+        } else {
+            const typename P::raw_t *q = base + ((size_t)ly * nx + lx) * P::NC;
+#pragma unroll
+            for (int ch = 0; ch < P::NC; ch++) o[ch] = __ldg(q + ch);
+        }
+    }
+};
+
+struct TmaAdvectArgs {
+    void *next_p;
+    const void *p;
+    const float2 *vel;
+    Geo g;
+    float dt;
+    int no_slip;
+    int vel_is_p;        // velocity advect: the velocity of a node is already in the staged tile
+    int store_tma;       // dye: write the tile with a bulk-tensor store
+    int *status;
+};
+
+template <class P>
+__global__ void __launch_bounds__(AT_THREADS)
+advect_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                  const TmaAdvectArgs a)
+{
+    using raw_t = typename P::raw_t;
+    using TS = TileShape<P>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    raw_t *tile = reinterpret_cast<raw_t *>(smem);
+    raw_t *otile = reinterpret_cast<raw_t *>(smem + ((TS::IN_BYTES + 127) & ~127));
+    __shared__ __align__(8) uint64_t bar;
+
+    const Geo &g = a.g;
+    const int tx0 = g.x0 + blockIdx.x * AT_TX, ty0 = g.y0 + blockIdx.y * AT_TY;   // tile origin (local)
+    const int bx0 = tx0 - AT_HALO, by0 = ty0 - AT_HALO;                           // staged box origin
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, TS::IN_BYTES);
+        tma_load_2d(tile, &in_map, bx0 * P::NC, by0, &bar);
+    }
+
+    // while the tile is in flight: velocities (dye advect) for this thread's nodes
+    constexpr int ROWS_PER_IT = AT_THREADS / AT_TX, ITERS = AT_TY / ROWS_PER_IT;
+    const int cx = threadIdx.x % AT_TX, cy = threadIdx.x / AT_TX;
+    float2 vel[ITERS];
+    if (!a.vel_is_p) {
+#pragma unroll
+        for (int it = 0; it < ITERS; it++) {
+            const int lx = tx0 + cx, ly = ty0 + cy + it * ROWS_PER_IT;
+            vel[it] = (lx < g.x1 && ly < g.y1) ? __ldg(a.vel + (size_t)ly * g.nx + lx) : make_float2(0.f, 0.f);
+        }
+    }
+    mbar_wait(&bar, 0);
+
+    TileFetch<P> fetch{tile, reinterpret_cast<const raw_t *>(a.p), bx0, by0, g.ox, g.oy, g.nx, g.ny, a.status};
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {
+        const int ry = cy + it * ROWS_PER_IT;
+        const int lx = tx0 + cx, ly = ty0 + ry;
+        const bool live = lx < g.x1 && ly < g.y1;
+        raw_t out[P::NC];
+#pragma unroll
+        for (int ch = 0; ch < P::NC; ch++) out[ch] = 0;
+        if (live) {
+            float2 vv;
+            if (a.vel_is_p) {
+                if constexpr (P::NC == 2)
+                    vv = *reinterpret_cast<const float2 *>(tile + (ry + AT_HALO) * TS::ROW_WORDS + (cx + AT_HALO) * 2);
+                else
+                    vv = make_float2(0.f, 0.f);
+            } else {
+                vv = vel[it];
+            }
+            float si, sj;
+            backtrace(si, sj, g.ox + lx, g.oy + ly, vv, a.dt);
+            sample<P>(out, fetch, si, sj, g.GX, g.GY, a.no_slip != 0);
+        }
+        if constexpr (P::NC == 2) {
+            if (live) reinterpret_cast<float2 *>(a.next_p)[(size_t)ly * g.nx + lx] = make_float2(out[0], out[1]);
+        } else {
+            if (a.store_tma) {
+                raw_t *q = otile + (ry * AT_TX + cx) * 3;
+                q[0] = out[0]; q[1] = out[1]; q[2] = out[2];
+            } else if (live) {
+                raw_t *q = reinterpret_cast<raw_t *>(a.next_p) + ((size_t)ly * g.nx + lx) * 3;
+                q[0] = out[0]; q[1] = out[1]; q[2] = out[2];
+            }
+        }
+    }
+    if constexpr (P::NC == 3) {
+        if (a.store_tma) {
+            // out_map describes the compute rectangle only, so the hardware clips partial tiles
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                tma_store_2d(&out_map, blockIdx.x * AT_TX * 3, blockIdx.y * AT_TY, otile);
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+
+template <class P>
+bool advect_tma_legal(const void *p, const Geo &g)
+{
+    // TMA: 16-byte aligned base and row pitch; boxes of at most 256 words
+    return ((uintptr_t)p % 16 == 0) && (((size_t)g.nx * P::NC * 4) % 16 == 0) && g.nx >= AT_TX && g.ny >= AT_TY &&
+           tma_encode_fn() != nullptr;
+}
+
+template <class P>
+static int launch_tma(const Launch &L, void *next_p, const void *p, const float2 *vel, const Geo &g, float dt,
+                      bool no_slip, int *status)
+{
+    using TS = TileShape<P>;
+    const int w = g.x1 - g.x0, h = g.y1 - g.y0;
+    if (w <= 0 || h <= 0) return 0;
+    CUtensorMap in_map, out_map;
+    if (!tma_make_map_2d(&in_map, p, (uint64_t)g.nx * P::NC, g.ny, (uint64_t)g.nx * P::NC, TS::ROW_WORDS, TS::H))
+        return (int)cudaErrorInvalidValue;
+    TmaAdvectArgs a;
+    a.next_p = next_p; a.p = p; a.vel = vel; a.g = g; a.dt = dt; a.no_slip = no_slip ? 1 : 0;
+    a.vel_is_p = (P::NC == 2 && (const void *)vel == p) ? 1 : 0;
+    a.status = status;
+    a.store_tma = 0;
+    out_map = in_map;
+    if (P::NC == 3) {
+        // the store map covers exactly the compute rectangle: base = its first node
+        const char *obase = (const char *)next_p + ((size_t)g.y0 * g.nx + g.x0) * 12;
+        if ((uintptr_t)obase % 16 == 0 &&
+            tma_make_map_2d(&out_map, obase, (uint64_t)w * 3, h, (uint64_t)g.nx * 3, AT_TX * 3, AT_TY))
+            a.store_tma = 1;
+    }
+    const size_t smem = ((TS::IN_BYTES + 127) & ~127) + TS::OUT_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(advect_tma_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((w + AT_TX - 1) / AT_TX, (h + AT_TY - 1) / AT_TY);
+    advect_tma_kernel<P><<<grid, AT_THREADS, smem, L.stream>>>(in_map, out_map, a);
+    ++*L.launches;
+    return (int)cudaGetLastError();
+}
+
+bool advect_vec2f_tma_legal(const float2 *p, const Geo &g) { return advect_tma_legal<Vec2Payload>(p, g); }
+bool advect_rgb_tma_legal(const uint32_t *c, const Geo &g) { return advect_tma_legal<RgbPayload>(c, g); }
+
+int launch_advect_vec2f_tma(const Launch &L, float2 *next_p, const float2 *p, const float2 *vel, const Geo &g,
+                            float dt, bool no_slip, int *status)
+{
+    return launch_tma<Vec2Payload>(L, next_p, p, vel, g, dt, no_slip, status);
+}
+
+int launch_advect_rgb_tma(const Launch &L, uint32_t *next_c, const uint32_t *c, const float2 *vel, const Geo &g,
+                          float dt, bool no_slip, int *status)
+{
+    return launch_tma<RgbPayload>(L, next_c, c, vel, g, dt, no_slip, status);
+}
+
+}  // namespace fs

@@ -9,6 +9,7 @@
 
 using namespace fs;
 
+constexpr int WORK_SLOTS = 64;
 enum Scratch { S_VTMP = 0, S_CTMP, S_DIV, S_P, S_P2, S_HV, S_HV2, S_HC, S_HC2, S_HP, S_HD, S_HIMG, S_EDRAG, S_ECNT, S_COUNT };
 
 struct fs_ctx {
@@ -20,6 +21,7 @@ struct fs_ctx {
     size_t scratch_bytes[S_COUNT];
     int *status_dev;            // device flag raised by tile advects (FS_ERR_HALO_OVERRUN)
     unsigned int *maxdisp_dev;  // max-displacement reduction cell
+    int *work_dev;              // WORK_SLOTS tile counters of the persistent SOR kernel (one per pass)
     size_t max_smem_optin;
     int opt_sor, opt_sor_t, opt_sor_shape, opt_advect, opt_fuse;
 };
@@ -105,6 +107,9 @@ Geo grown(const Geo &g, int r)
 int core_advect_vec2f(fs_ctx *ctx, fs_vec2f *next_p, const fs_vec2f *p, const fs_vec2f *vel,
                       const Geo &g, float dt, int no_slip, int *status)
 {
+    if (ctx->opt_advect == 1 && advect_vec2f_tma_legal((const float2 *)p, g))
+        return launch_advect_vec2f_tma(mk(ctx), (float2 *)next_p, (const float2 *)p, (const float2 *)vel, g,
+                                       dt, no_slip != 0, status);
     return launch_advect_vec2f_gather(mk(ctx), (float2 *)next_p, (const float2 *)p,
                                       (const float2 *)vel, g, dt, no_slip != 0, status);
 }
@@ -112,6 +117,9 @@ int core_advect_vec2f(fs_ctx *ctx, fs_vec2f *next_p, const fs_vec2f *p, const fs
 int core_advect_rgb(fs_ctx *ctx, fs_rgb_uq32 *next_c, const fs_rgb_uq32 *c, const fs_vec2f *vel,
                     const Geo &g, float dt, int no_slip, int *status)
 {
+    if (ctx->opt_advect == 1 && advect_rgb_tma_legal((const uint32_t *)c, g))
+        return launch_advect_rgb_tma(mk(ctx), (uint32_t *)next_c, (const uint32_t *)c, (const float2 *)vel, g,
+                                     dt, no_slip != 0, status);
     return launch_advect_rgb_gather(mk(ctx), (uint32_t *)next_c, (const uint32_t *)c,
                                     (const float2 *)vel, g, dt, no_slip != 0, status);
 }
@@ -135,8 +143,10 @@ int core_poisson_solve(fs_ctx *ctx, float *p, const float *div, const Geo &g, fl
         for (int k = 0; k < passes; k++) {
             const int t = iters - done < T ? iters - done : T;
             float *dst = bufs[k & 1];
+            if (k % WORK_SLOTS == 0)  // one zeroed tile counter per pass of the persistent kernel
+                FS_CUDA_TRY(cudaMemsetAsync(ctx->work_dev, 0, WORK_SLOTS * sizeof(int), ctx->stream));
             if ((e = launch_sor_blocked(mk(ctx), dst, src, div, g, dx, omega, 0, 2 * t,
-                                        ctx->opt_sor_shape)))
+                                        ctx->opt_sor_shape, ctx->work_dev + k % WORK_SLOTS)))
                 return e;
             src = dst;
             done += t;
@@ -212,11 +222,12 @@ int fs_ctx_create(fs_ctx **out, int device, void *stream)
     ctx->max_smem_optin = prop.sharedMemPerBlockOptin;
     ctx->opt_sor = 1;
     ctx->opt_sor_t = 8;
-    ctx->opt_sor_shape = 0;
+    ctx->opt_sor_shape = 3;
     ctx->opt_advect = 1;
     ctx->opt_fuse = 1;
     cudaError_t e = cudaMalloc(&ctx->status_dev, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->maxdisp_dev, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->work_dev, WORK_SLOTS * sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(ctx->status_dev, 0, sizeof(int));
     if (e != cudaSuccess) {
         delete ctx;
@@ -235,6 +246,7 @@ int fs_ctx_destroy(fs_ctx *ctx)
         if (ctx->scratch[s]) cudaFree(ctx->scratch[s]);
     cudaFree(ctx->status_dev);
     cudaFree(ctx->maxdisp_dev);
+    cudaFree(ctx->work_dev);
     delete ctx;
     return FS_OK;
 }
@@ -623,9 +635,11 @@ int fs_tile_sor_sweeps(float *p_out, const float *p_in, const float *div, const 
         return FS_ERR_INVALID_ARG;
     DeviceGuard guard(ctx->device);
     const Geo g = geo_tile(*t);
-    if (ctx->opt_sor == 1 && n_half > 0 && n_half <= SOR_BLOCKED_MAX_HALF)
+    if (ctx->opt_sor == 1 && n_half > 0 && n_half <= SOR_BLOCKED_MAX_HALF) {
+        FS_CUDA_TRY(cudaMemsetAsync(ctx->work_dev, 0, sizeof(int), ctx->stream));
         return launch_sor_blocked(mk(ctx), p_out, p_in, div, g, dx, omega, first_parity, n_half,
-                                  ctx->opt_sor_shape);
+                                  ctx->opt_sor_shape, ctx->work_dev);
+    }
     // seed p_out on the rectangle grown by n_half, then sweep in place on
     // rectangles that shrink by one node per half-sweep
     const Geo seed = grown(g, n_half);

@@ -20,6 +20,14 @@ int launch_advect_vec2f_gather(const Launch &L, float2 *next_p, const float2 *p,
 int launch_advect_rgb_gather(const Launch &L, uint32_t *next_c, const uint32_t *c, const float2 *vel,
                              const Geo &g, float dt, bool no_slip, int *status);
 
+// advect_tma.cu — same operator, source tile staged in shared memory by TMA (needs 16-byte row pitch)
+bool advect_vec2f_tma_legal(const float2 *p, const Geo &g);
+bool advect_rgb_tma_legal(const uint32_t *c, const Geo &g);
+int launch_advect_vec2f_tma(const Launch &L, float2 *next_p, const float2 *p, const float2 *vel,
+                            const Geo &g, float dt, bool no_slip, int *status);
+int launch_advect_rgb_tma(const Launch &L, uint32_t *next_c, const uint32_t *c, const float2 *vel,
+                          const Geo &g, float dt, bool no_slip, int *status);
+
 // stencil.cu — finitediff.cpp:9-82, ino:264-269
 int launch_divergence(const Launch &L, float *div, const float2 *v, const Geo &g, float dx);
 int launch_subtract_gradient(const Launch &L, float2 *v_out, const float2 *v_in, const float *p,
@@ -32,10 +40,11 @@ int launch_sor_half_sweep(const Launch &L, float *p, const float *div, const Geo
                           float omega, int parity);
 
 // sor_blocked.cu — `n_half` colour half-sweeps per HBM round trip, p_in -> p_out (distinct
-// buffers; p_in == nullptr means all zero).  shape 0 = 128x96 region, 2 CTAs/SM; 1 = 128x192, 1 CTA/SM.
+// buffers; p_in == nullptr means all zero).  shape 0 = 128x96 region, 2 CTAs/SM; 1 = 128x192, 1 CTA/SM;
+// 2/3 = the same regions with persistent CTAs and TMA prefetch (need a ZEROED device work counter).
 constexpr int SOR_BLOCKED_MAX_HALF = 16;
 int launch_sor_blocked(const Launch &L, float *p_out, const float *p_in, const float *div, const Geo &g,
-                       float dx, float omega, int first_parity, int n_half, int shape);
+                       float dx, float omega, int first_parity, int n_half, int shape, int *work_counter);
 
 // ensemble.cu — whole loop() body per grid, resident in shared memory
 size_t ensemble_smem_bytes(int dim_x, int dim_y);

@@ -21,11 +21,19 @@
 // aside, every stored value is computed by the same operations in the same order
 // as poisson.cpp — the result is bit-identical to the reference for any H.
 //
+// Two loaders feed the same sweep code:
+//   sor_blocked_kernel      one tile per CTA, region read straight from global into registers
+//                           (any pitch/alignment; the fallback);
+//   sor_blocked_tma_kernel  persistent CTAs; while tile k is swept out of registers, the bulk-
+//                           tensor loads (TMA, SASS UTMALDG) of tile k+1's p and d regions land in
+//                           shared memory, hiding the DRAM latency behind 2T half-sweeps.
+//
 // Traffic per pass: read p + d over the region, write p over the tile, i.e.
 // ~(8*redundancy + 4) B/node for H/2 full iterations instead of 12 B per
 // iteration per colour sector.
 #include "kernels.h"
 #include "sor.cuh"
+#include "tma.cuh"
 
 namespace fs {
 
@@ -66,35 +74,124 @@ __device__ __forceinline__ void strip_half_sweep(float (&p)[R][4], const float (
                                                  const float (&dn)[4], const float (&up)[4],
                                                  const SorCoef &k, int gi0, int gj0, int GX, int GY)
 {
+    // In a region that touches a wall, only the rows at/after a horizontal wall (warp-uniform) and
+    // the lanes whose four columns reach a vertical wall need the per-node wall logic.
+    const bool lane_generic = WALL && (gi0 <= 0 || gi0 + 3 >= GX - 1);
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int gj = gj0 + r;
+        const bool generic = WALL && (lane_generic || gj <= 0 || gj >= GY - 1);
         if (((r + Q) & 1) == 0) {
             const float lft = __shfl_up_sync(0xffffffffu, p[r][3], 1);
             const float d0 = r > 0 ? p[r > 0 ? r - 1 : 0][0] : dn[0], u0 = r < R - 1 ? p[r < R - 1 ? r + 1 : 0][0] : up[0];
             const float d2 = r > 0 ? p[r > 0 ? r - 1 : 0][2] : dn[2], u2 = r < R - 1 ? p[r < R - 1 ? r + 1 : 0][2] : up[2];
-            const float n0 = update_node<WALL>(p[r][0], lft, p[r][1], d0, u0, dxd[r][0], k, gi0 + 0, gj, GX, GY);
-            const float n2 = update_node<WALL>(p[r][2], p[r][1], p[r][3], d2, u2, dxd[r][2], k, gi0 + 2, gj, GX, GY);
+            float n0, n2;
+            if (generic) {
+                n0 = update_node<true>(p[r][0], lft, p[r][1], d0, u0, dxd[r][0], k, gi0 + 0, gj, GX, GY);
+                n2 = update_node<true>(p[r][2], p[r][1], p[r][3], d2, u2, dxd[r][2], k, gi0 + 2, gj, GX, GY);
+            } else {
+                n0 = sor_update_interior(p[r][0], lft, p[r][1], d0, u0, dxd[r][0], k);
+                n2 = sor_update_interior(p[r][2], p[r][1], p[r][3], d2, u2, dxd[r][2], k);
+            }
             p[r][0] = n0;
             p[r][2] = n2;
         } else {
             const float rgt = __shfl_down_sync(0xffffffffu, p[r][0], 1);
             const float d1 = r > 0 ? p[r > 0 ? r - 1 : 0][1] : dn[1], u1 = r < R - 1 ? p[r < R - 1 ? r + 1 : 0][1] : up[1];
             const float d3 = r > 0 ? p[r > 0 ? r - 1 : 0][3] : dn[3], u3 = r < R - 1 ? p[r < R - 1 ? r + 1 : 0][3] : up[3];
-            const float n1 = update_node<WALL>(p[r][1], p[r][0], p[r][2], d1, u1, dxd[r][1], k, gi0 + 1, gj, GX, GY);
-            const float n3 = update_node<WALL>(p[r][3], p[r][2], rgt, d3, u3, dxd[r][3], k, gi0 + 3, gj, GX, GY);
+            float n1, n3;
+            if (generic) {
+                n1 = update_node<true>(p[r][1], p[r][0], p[r][2], d1, u1, dxd[r][1], k, gi0 + 1, gj, GX, GY);
+                n3 = update_node<true>(p[r][3], p[r][2], rgt, d3, u3, dxd[r][3], k, gi0 + 3, gj, GX, GY);
+            } else {
+                n1 = sor_update_interior(p[r][1], p[r][0], p[r][2], d1, u1, dxd[r][1], k);
+                n3 = sor_update_interior(p[r][3], p[r][2], rgt, d3, u3, dxd[r][3], k);
+            }
             p[r][1] = n1;
             p[r][3] = n3;
         }
     }
 }
 
+// all H half-sweeps of one pass over a warp's strip, with the inter-warp row mailbox
 template <int R, int NW, bool WALL>
-__device__ __forceinline__ void run_pass(const BlockedArgs &a, float4 (*mail)[NW][2][32])
+__device__ __forceinline__ void sweep_pass(float (&p)[R][4], const float (&dxd)[R][4], const BlockedArgs &a,
+                                           float4 (*mail)[NW][2][32], int gi0, int gj0)
 {
     const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+    // colour bookkeeping: node (column c, row r) of this strip has global parity (c + r + pb) & 1
+    const int pb = (gi0 + gj0) & 1;
+    float dn[4] = {0.f, 0.f, 0.f, 0.f}, up[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < a.n_half; s++) {
+        const int buf = s & 1;
+        mail[buf][w][0][t] = make_float4(p[0][0], p[0][1], p[0][2], p[0][3]);
+        mail[buf][w][1][t] = make_float4(p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3]);
+        __syncthreads();
+        if (w > 0) {
+            const float4 q = mail[buf][w - 1][1][t];
+            dn[0] = q.x; dn[1] = q.y; dn[2] = q.z; dn[3] = q.w;
+        }
+        if (w < NW - 1) {
+            const float4 q = mail[buf][w + 1][0][t];
+            up[0] = q.x; up[1] = q.y; up[2] = q.z; up[3] = q.w;
+        }
+        const int q_eff = (a.first_parity + s + pb) & 1;
+        if (q_eff == 0) strip_half_sweep<R, 0, WALL>(p, dxd, dn, up, a.k, gi0, gj0, a.g.GX, a.g.GY);
+        else            strip_half_sweep<R, 1, WALL>(p, dxd, dn, up, a.k, gi0, gj0, a.g.GX, a.g.GY);
+    }
+}
+
+// write back the tile interior, clipped to the compute rectangle
+template <int R>
+__device__ __forceinline__ void store_tile(const float (&p)[R][4], const BlockedArgs &a, int rlx0, int rly0,
+                                           int lx0, int ly0)
+{
     const Geo &g = a.g;
-    // region origin (local) and this thread's first column / this warp's first row
+    const int ox0 = max(rlx0 + a.hpx, g.x0), ox1 = min(rlx0 + a.hpx + a.tw_out, g.x1);
+    const int oy0 = max(rly0 + a.hpy, g.y0), oy1 = min(rly0 + a.hpy + a.th_out, g.y1);
+    const bool cols_full = lx0 >= ox0 && lx0 + 3 < ox1;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int ly = ly0 + r;
+        if (ly < oy0 || ly >= oy1) continue;
+        float *row = a.p_out + (size_t)ly * g.nx;
+        if (cols_full && a.vec_ok) {
+            *reinterpret_cast<float4 *>(row + lx0) = make_float4(p[r][0], p[r][1], p[r][2], p[r][3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (lx0 + c >= ox0 && lx0 + c < ox1) row[lx0 + c] = p[r][c];
+        }
+    }
+}
+
+// Work order of the persistent kernel: the frame of tiles along the window's edge first (they
+// are the ones that can touch a wall and take the slower path), then the interior, row by row.
+__device__ __forceinline__ void tile_coords(int idx, int ntx, int nty, int &tx, int &ty)
+{
+    if (ntx < 3 || nty < 3) { tx = idx % ntx; ty = idx / ntx; return; }
+    const int frame = 2 * ntx + 2 * (nty - 2);
+    if (idx < ntx) { tx = idx; ty = 0; }
+    else if (idx < 2 * ntx) { tx = idx - ntx; ty = nty - 1; }
+    else if (idx < frame) { const int k = idx - 2 * ntx; tx = (k & 1) ? ntx - 1 : 0; ty = 1 + (k >> 1); }
+    else { const int k = idx - frame; tx = 1 + k % (ntx - 2); ty = 1 + k / (ntx - 2); }
+}
+
+// does a region touch a domain wall or stick out of the domain?  (CTA-uniform)
+template <int R, int NW>
+__device__ __forceinline__ bool region_hits_wall(const BlockedArgs &a, int rlx0, int rly0)
+{
+    const int rgx0 = a.g.ox + rlx0, rgy0 = a.g.oy + rly0;
+    return rgx0 <= 0 || rgy0 <= 0 || rgx0 + BLK_RW >= a.g.GX || rgy0 + R * NW >= a.g.GY;
+}
+
+// ---- loader 1: one tile per CTA, region read straight from global into registers ---------------
+template <int R, int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB) sor_blocked_kernel(const BlockedArgs a)
+{
+    __shared__ float4 mail[2][NW][2][32];
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+    const Geo &g = a.g;
     const int rlx0 = a.lax + (int)blockIdx.x * a.tw_out - a.hpx;
     const int rly0 = a.lay + (int)blockIdx.y * a.th_out - a.hpy;
     const int lx0 = rlx0 + 4 * t, ly0 = rly0 + w * R;
@@ -129,81 +226,141 @@ __device__ __forceinline__ void run_pass(const BlockedArgs &a, float4 (*mail)[NW
             }
         }
     }
-
-    // colour bookkeeping: node (column c, row r) of this strip has global parity (c + r + pb) & 1
-    const int pb = (gi0 + gj0) & 1;
-    float dn[4] = {0.f, 0.f, 0.f, 0.f}, up[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < a.n_half; s++) {
-        const int buf = s & 1;
-        mail[buf][w][0][t] = make_float4(p[0][0], p[0][1], p[0][2], p[0][3]);
-        mail[buf][w][1][t] = make_float4(p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3]);
-        __syncthreads();
-        if (w > 0) {
-            const float4 q = mail[buf][w - 1][1][t];
-            dn[0] = q.x; dn[1] = q.y; dn[2] = q.z; dn[3] = q.w;
-        }
-        if (w < NW - 1) {
-            const float4 q = mail[buf][w + 1][0][t];
-            up[0] = q.x; up[1] = q.y; up[2] = q.z; up[3] = q.w;
-        }
-        const int q_eff = (a.first_parity + s + pb) & 1;
-        if (q_eff == 0) strip_half_sweep<R, 0, WALL>(p, dxd, dn, up, a.k, gi0, gj0, g.GX, g.GY);
-        else            strip_half_sweep<R, 1, WALL>(p, dxd, dn, up, a.k, gi0, gj0, g.GX, g.GY);
-    }
-
-    // write back the tile interior, clipped to the compute rectangle
-    const int ox0 = max(rlx0 + a.hpx, g.x0), ox1 = min(rlx0 + a.hpx + a.tw_out, g.x1);
-    const int oy0 = max(rly0 + a.hpy, g.y0), oy1 = min(rly0 + a.hpy + a.th_out, g.y1);
-    const bool cols_full = lx0 >= ox0 && lx0 + 3 < ox1;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        const int ly = ly0 + r;
-        if (ly < oy0 || ly >= oy1) continue;
-        float *row = a.p_out + (size_t)ly * g.nx;
-        if (cols_full && a.vec_ok) {
-            *reinterpret_cast<float4 *>(row + lx0) = make_float4(p[r][0], p[r][1], p[r][2], p[r][3]);
-        } else {
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-                if (lx0 + c >= ox0 && lx0 + c < ox1) row[lx0 + c] = p[r][c];
-        }
-    }
+    if (!region_hits_wall<R, NW>(a, rlx0, rly0)) sweep_pass<R, NW, false>(p, dxd, a, mail, gi0, gj0);
+    else                                          sweep_pass<R, NW, true>(p, dxd, a, mail, gi0, gj0);
+    store_tile<R>(p, a, rlx0, rly0, lx0, ly0);
 }
 
+// ---- loader 2: persistent CTAs, next tile prefetched into shared memory by TMA -----------------
+// The hardware zero-fills the parts of a region outside the window — exactly what loader 1 does by
+// hand.
 template <int R, int NW, int MINB>
-__global__ void __launch_bounds__(32 * NW, MINB) sor_blocked_kernel(const BlockedArgs a)
+__global__ void __launch_bounds__(32 * NW, MINB)
+sor_blocked_tma_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant__ CUtensorMap d_map,
+                       const BlockedArgs a, int ntx, int nty, int *work_counter)
 {
-    __shared__ float4 mail[2][NW][2][32];
-    // does the region touch a domain wall or stick out of the domain?  (CTA-uniform)
-    const int rgx0 = a.g.ox + a.lax + (int)blockIdx.x * a.tw_out - a.hpx;
-    const int rgy0 = a.g.oy + a.lay + (int)blockIdx.y * a.th_out - a.hpy;
-    const bool wall = rgx0 <= 0 || rgy0 <= 0 || rgx0 + BLK_RW >= a.g.GX || rgy0 + R * NW >= a.g.GY;
-    if (!wall) run_pass<R, NW, false>(a, mail);
-    else       run_pass<R, NW, true>(a, mail);
-}
-
-template <int R, int NW, int MINB>
-static int launch_cfg(const Launch &L, BlockedArgs &a)
-{
+    constexpr int RH = R * NW;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4 *sd = reinterpret_cast<float4 *>(smem);                        // [RH][32] float4 = d region
+    float4 *sp = sd + RH * 32;                                            // p region
+    float4 (*mail)[NW][2][32] = reinterpret_cast<float4 (*)[NW][2][32]>(sp + RH * 32);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int s_tile[2];
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
     const Geo &g = a.g;
+    const bool has_p = a.p_in != nullptr;
+    const uint32_t tx_bytes = (has_p ? 2u : 1u) * RH * BLK_RW * 4u;
+    const int n_tiles = ntx * nty;
+
+    // thread 0: claim the next tile (dynamic: wall tiles cost more than interior ones) and start
+    // its bulk-tensor loads
+    auto claim_and_prefetch = [&](int slot) {
+        const int idx = atomicAdd(work_counter, 1);
+        s_tile[slot] = idx;
+        if (idx < n_tiles) {
+            int tx, ty;
+            tile_coords(idx, ntx, nty, tx, ty);
+            const int x = a.lax + tx * a.tw_out - a.hpx, y = a.lay + ty * a.th_out - a.hpy;
+            mbar_expect_tx(&bar, tx_bytes);
+            tma_load_2d(sd, &d_map, x, y, &bar);
+            if (has_p) tma_load_2d(sp, &p_map, x, y, &bar);
+        }
+    };
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        claim_and_prefetch(0);
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    for (int it = 0;; it++) {
+        const int idx = s_tile[it & 1];
+        if (idx >= n_tiles) break;
+        int tx, ty;
+        tile_coords(idx, ntx, nty, tx, ty);
+        const int rlx0 = a.lax + tx * a.tw_out - a.hpx;
+        const int rly0 = a.lay + ty * a.th_out - a.hpy;
+        const int lx0 = rlx0 + 4 * t, ly0 = rly0 + w * R;
+        const int gi0 = g.ox + lx0, gj0 = g.oy + ly0;
+
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        float p[R][4], dxd[R][4];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float4 dv = sd[(w * R + r) * 32 + t];
+            dxd[r][0] = __fmul_rn(a.k.dx, dv.x);
+            dxd[r][1] = __fmul_rn(a.k.dx, dv.y);
+            dxd[r][2] = __fmul_rn(a.k.dx, dv.z);
+            dxd[r][3] = __fmul_rn(a.k.dx, dv.w);
+            if (has_p) {
+                const float4 pv = sp[(w * R + r) * 32 + t];
+                p[r][0] = pv.x; p[r][1] = pv.y; p[r][2] = pv.z; p[r][3] = pv.w;
+            } else {
+                p[r][0] = p[r][1] = p[r][2] = p[r][3] = 0.0f;
+            }
+        }
+        __syncthreads();                       // every warp has drained the staging buffers
+        if (threadIdx.x == 0) claim_and_prefetch((it + 1) & 1);   // visible after sweep_pass's first barrier
+        if (!region_hits_wall<R, NW>(a, rlx0, rly0)) sweep_pass<R, NW, false>(p, dxd, a, mail, gi0, gj0);
+        else                                          sweep_pass<R, NW, true>(p, dxd, a, mail, gi0, gj0);
+        store_tile<R>(p, a, rlx0, rly0, lx0, ly0);
+    }
+}
+
+template <int R, int NW>
+static bool tile_cfg(BlockedArgs &a, int &ntx, int &nty)
+{
     const int H = a.n_half;
     a.hpx = (H + 3) & ~3;
     a.hpy = H;
     a.tw_out = BLK_RW - 2 * a.hpx;
     a.th_out = R * NW - 2 * a.hpy;
-    if (a.tw_out <= 0 || a.th_out <= 0) return (int)cudaErrorInvalidValue;
-    a.lax = g.x0 & ~3;  // keep every region origin a multiple of 4 columns (float4 alignment)
-    a.lay = g.y0;
-    const int ntx = (g.x1 - a.lax + a.tw_out - 1) / a.tw_out;
-    const int nty = (g.y1 - a.lay + a.th_out - 1) / a.th_out;
+    a.lax = a.g.x0 & ~3;  // keep every region origin a multiple of 4 columns (float4 alignment)
+    a.lay = a.g.y0;
+    if (a.tw_out <= 0 || a.th_out <= 0) return false;
+    ntx = (a.g.x1 - a.lax + a.tw_out - 1) / a.tw_out;
+    nty = (a.g.y1 - a.lay + a.th_out - 1) / a.th_out;
+    return true;
+}
+
+template <int R, int NW, int MINB>
+static int launch_cfg(const Launch &L, BlockedArgs &a)
+{
+    int ntx, nty;
+    if (!tile_cfg<R, NW>(a, ntx, nty)) return (int)cudaErrorInvalidValue;
     if (ntx <= 0 || nty <= 0) return 0;
     sor_blocked_kernel<R, NW, MINB><<<dim3(ntx, nty), 32 * NW, 0, L.stream>>>(a);
     ++*L.launches;
     return (int)cudaGetLastError();
 }
 
+template <int R, int NW, int MINB>
+static int launch_cfg_tma(const Launch &L, BlockedArgs &a, int *work_counter)
+{
+    const Geo &g = a.g;
+    int ntx, nty;
+    if (!tile_cfg<R, NW>(a, ntx, nty)) return (int)cudaErrorInvalidValue;
+    if (ntx <= 0 || nty <= 0) return 0;
+    CUtensorMap p_map, d_map;
+    if (!tma_make_map_2d(&d_map, a.div, g.nx, g.ny, g.nx, BLK_RW, R * NW)) return (int)cudaErrorInvalidValue;
+    p_map = d_map;
+    if (a.p_in && !tma_make_map_2d(&p_map, a.p_in, g.nx, g.ny, g.nx, BLK_RW, R * NW))
+        return (int)cudaErrorInvalidValue;
+    const size_t smem = (size_t)2 * R * NW * BLK_RW * 4 + sizeof(float4) * 2 * NW * 2 * 32;
+    cudaError_t e = cudaFuncSetAttribute(sor_blocked_tma_kernel<R, NW, MINB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int n_tiles = ntx * nty;
+    const int grid = n_tiles < MINB * L.num_sms ? n_tiles : MINB * L.num_sms;
+    sor_blocked_tma_kernel<R, NW, MINB><<<grid, 32 * NW, smem, L.stream>>>(p_map, d_map, a, ntx, nty, work_counter);
+    ++*L.launches;
+    return (int)cudaGetLastError();
+}
+
 int launch_sor_blocked(const Launch &L, float *p_out, const float *p_in, const float *div, const Geo &g,
-                       float dx, float omega, int first_parity, int n_half, int shape)
+                       float dx, float omega, int first_parity, int n_half, int shape, int *work_counter)
 {
     if (g.x1 <= g.x0 || g.y1 <= g.y0 || n_half <= 0) return 0;
     if (n_half > SOR_BLOCKED_MAX_HALF) return (int)cudaErrorInvalidValue;
@@ -217,8 +374,13 @@ int launch_sor_blocked(const Launch &L, float *p_out, const float *p_in, const f
     a.n_half = n_half;
     a.vec_ok = (g.nx % 4 == 0) && ((uintptr_t)p_out % 16 == 0) && ((uintptr_t)div % 16 == 0) &&
                (!p_in || (uintptr_t)p_in % 16 == 0);
+    const bool tma_ok = a.vec_ok && work_counter && tma_encode_fn() != nullptr;
     switch (shape) {
         case 1: return launch_cfg<12, 16, 1>(L, a);  // 128 x 192 region, one CTA per SM
+        case 2:                                      // 128 x 96 region, persistent, TMA-prefetched
+            return tma_ok ? launch_cfg_tma<12, 8, 2>(L, a, work_counter) : launch_cfg<12, 8, 2>(L, a);
+        case 3:                                      // 128 x 192 region, persistent, TMA-prefetched
+            return tma_ok ? launch_cfg_tma<12, 16, 1>(L, a, work_counter) : launch_cfg<12, 16, 1>(L, a);
         default: return launch_cfg<12, 8, 2>(L, a);  // 128 x 96 region, two CTAs per SM
     }
 }

@@ -62,7 +62,10 @@ int  fs_ctx_synchronize(fs_ctx *ctx);
 /* Kernel-variant switches for A/B measurement (all variants are bit-identical):
  *   "sor"    : 0 = one half-sweep per launch, 1 = shared-memory temporally blocked (default)
  *   "sor_t"  : full iterations fused per HBM round trip (1..8, default 8)
- *   "sor_shape": 0 = 128x96-node region, two CTAs per SM (default); 1 = 128x192, one CTA per SM
+ *   "sor_shape": CTA region and loader of the blocked solver: 0 = 128x96 nodes, 1 = 128x192, both
+ *              loaded straight from global; 2 / 3 = the same regions with persistent CTAs whose
+ *              next tile is prefetched by TMA (3 is the default; falls back to 1 when rows are
+ *              not 16-byte multiples)
  *   "advect" : 0 = direct L1/L2 gather, 1 = TMA-staged shared-memory tile (default where legal)
  *   "fuse"   : 0 = fs_step runs the operators one by one, 1 = divergence/gradient fused into SOR passes */
 int  fs_ctx_set_option(fs_ctx *ctx, const char *name, int value);

@@ -95,18 +95,21 @@ def test_poisson_solve(ctx, oracle, sor_variant, shape, iters, omega, dx):
     assert_bit_equal(to_host(p), oracle.poisson_solve(d, dx, iters, omega), "pressure")
 
 
+@pytest.mark.parametrize("shape", [0, 1, 2, 3], ids=["direct-96", "direct-192", "tma-96", "tma-192"])
 @pytest.mark.parametrize("t_block", [1, 2, 3, 4, 6, 8])
-def test_poisson_solve_every_blocking_depth(ctx, oracle, t_block):
+def test_poisson_solve_every_blocking_depth(ctx, oracle, t_block, shape):
     ctx.set_option("sor", 1)
     ctx.set_option("sor_t", t_block)
+    ctx.set_option("sor_shape", shape)
     try:
-        for dim_x, dim_y, iters in [(300, 200, 13), (61, 81, 10), (1000, 40, 9)]:
+        for dim_x, dim_y, iters in [(300, 200, 13), (61, 81, 10), (1000, 40, 9), (1024, 1100, 17)]:
             d = np.random.default_rng(7).normal(0, 20, (dim_y, dim_x)).astype(np.float32)
             p = torch.empty(dim_y, dim_x, dtype=torch.float32, device="cuda")
             ctx.poisson_solve(p, to_dev(d), dim_x, dim_y, 1.0, iters, 1.96)
             assert_bit_equal(to_host(p), oracle.poisson_solve(d, 1.0, iters, 1.96), f"T={t_block}")
     finally:
         ctx.set_option("sor_t", 8)
+        ctx.set_option("sor_shape", 3)
 
 
 def test_half_sweep_colours(ctx, oracle):
