@@ -28,6 +28,11 @@
 //                           tensor loads (TMA, SASS UTMALDG) of tile k+1's p and d regions land in
 //                           shared memory, hiding the DRAM latency behind 2T half-sweeps.
 //
+// (A packed-f32x2 version of the sweep — FADD2/FMUL2, two nodes per instruction — was built and
+// measured: bit-exact but 15 % SLOWER on B200 (packed ops issue at half rate and the pack/unpack
+// moves serialise the row chains); profiles/r01_kernel_sweep_packed_f32x2_rejected.json.  Also note
+// that ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false.)
+//
 // Traffic per pass: read p + d over the region, write p over the tile, i.e.
 // ~(8*redundancy + 4) B/node for H/2 full iterations instead of 12 B per
 // iteration per colour sector.
@@ -381,6 +386,12 @@ int launch_sor_blocked(const Launch &L, float *p_out, const float *p_in, const f
             return tma_ok ? launch_cfg_tma<12, 8, 2>(L, a, work_counter) : launch_cfg<12, 8, 2>(L, a);
         case 3:                                      // 128 x 192 region, persistent, TMA-prefetched
             return tma_ok ? launch_cfg_tma<12, 16, 1>(L, a, work_counter) : launch_cfg<12, 16, 1>(L, a);
+        case 4:                                      // 128 x 144 region, 12 warps (up to 168 registers)
+            return tma_ok ? launch_cfg_tma<12, 12, 1>(L, a, work_counter) : launch_cfg<12, 16, 1>(L, a);
+        case 5:                                      // 128 x 160 region, 16 warps x 10 rows
+            return tma_ok ? launch_cfg_tma<10, 16, 1>(L, a, work_counter) : launch_cfg<12, 16, 1>(L, a);
+        case 6:                                      // 128 x 192 region, 12 warps x 16 rows
+            return tma_ok ? launch_cfg_tma<16, 12, 1>(L, a, work_counter) : launch_cfg<12, 16, 1>(L, a);
         default: return launch_cfg<12, 8, 2>(L, a);  // 128 x 96 region, two CTAs per SM
     }
 }

@@ -13,13 +13,10 @@ namespace fs {
 
 constexpr int ST_BX = 64, ST_BY = 4;
 
-// calculate_divergence, finitediff.cpp:33-39
-__global__ void __launch_bounds__(ST_BX *ST_BY)
-divergence_kernel(float *__restrict__ div, const float2 *__restrict__ v, Geo g, float two_dx_inv)
+// one node of calculate_divergence, finitediff.cpp:9-31
+__device__ __forceinline__ float div_node(const float2 *__restrict__ v, const Geo &g, int lx, int ly,
+                                          float two_dx_inv)
 {
-    const int lx = g.x0 + blockIdx.x * ST_BX + threadIdx.x;
-    const int ly = g.y0 + blockIdx.y * ST_BY + threadIdx.y;
-    if (lx >= g.x1 || ly >= g.y1) return;
     const size_t l = (size_t)ly * g.nx + lx;
     const int gi = g.ox + lx, gj = g.oy + ly;
     const int i_max = g.GX - 1, j_max = g.GY - 1;
@@ -37,17 +34,73 @@ divergence_kernel(float *__restrict__ div, const float2 *__restrict__ v, Geo g, 
         s = __fadd_rn(s, gj > 0 ? -__ldg(&v[l - g.nx].y) : c.y);
         s = __fadd_rn(s, gj < j_max ? __ldg(&v[l + g.nx].y) : -c.y);
     }
-    div[l] = __fmul_rn(s, two_dx_inv);
+    return __fmul_rn(s, two_dx_inv);
 }
 
-// subtract_gradient, finitediff.cpp:41-82 (in place: only v[ij] itself is read)
+// calculate_divergence, finitediff.cpp:33-39 — one node per thread (any pitch / alignment)
 __global__ void __launch_bounds__(ST_BX *ST_BY)
-subtract_gradient_kernel(float2 *v_out, const float2 *v_in, const float *__restrict__ p, Geo g,
-                         float two_dx_inv)
+divergence_kernel(float *__restrict__ div, const float2 *__restrict__ v, Geo g, float two_dx_inv)
 {
     const int lx = g.x0 + blockIdx.x * ST_BX + threadIdx.x;
     const int ly = g.y0 + blockIdx.y * ST_BY + threadIdx.y;
     if (lx >= g.x1 || ly >= g.y1) return;
+    div[(size_t)ly * g.nx + lx] = div_node(v, g, lx, ly, two_dx_inv);
+}
+
+// Four consecutive nodes per thread: 6 independent 16-byte loads in flight per thread (the one-node
+// kernel was latency-bound with ~12 KB in flight per SM, ncu long_scoreboard 19.8 — profiles/
+// r01_ncu_stencils_v1.json), the two horizontal neighbours that belong to the adjacent lanes come
+// by warp shuffle, the result leaves as one 16-byte store.  Needs nx % 4 == 0 and 16-byte bases.
+constexpr int X4_ROWS = 8;
+__global__ void __launch_bounds__(32 * X4_ROWS)
+divergence_x4_kernel(float *__restrict__ div, const float2 *__restrict__ v, Geo g, float two_dx_inv)
+{
+    const int lane = threadIdx.x;
+    const int lx4 = (g.x0 & ~3) + 4 * (blockIdx.x * 32 + lane);
+    const int ly = g.y0 + blockIdx.y * X4_ROWS + threadIdx.y;
+    if (ly >= g.y1) return;                                  // warp-uniform
+    const size_t l = (size_t)ly * g.nx + lx4;
+    const int gi0 = g.ox + lx4, gj = g.oy + ly;
+    const bool can_load = lx4 + 3 < g.nx;
+    // all four nodes inside the rectangle and strictly interior to the domain
+    const bool fast = can_load && lx4 >= g.x0 && lx4 + 3 < g.x1 && gi0 > 0 && gi0 + 3 < g.GX - 1 && gj > 0 &&
+                      gj < g.GY - 1;
+    float4 c01 = make_float4(0.f, 0.f, 0.f, 0.f), c23 = c01, d01 = c01, d23 = c01, u01 = c01, u23 = c01;
+    if (can_load) {
+        c01 = __ldg(reinterpret_cast<const float4 *>(v + l));
+        c23 = __ldg(reinterpret_cast<const float4 *>(v + l + 2));
+    }
+    if (fast) {
+        d01 = __ldg(reinterpret_cast<const float4 *>(v + l - g.nx));
+        d23 = __ldg(reinterpret_cast<const float4 *>(v + l - g.nx + 2));
+        u01 = __ldg(reinterpret_cast<const float4 *>(v + l + g.nx));
+        u23 = __ldg(reinterpret_cast<const float4 *>(v + l + g.nx + 2));
+    }
+    float left_x = __shfl_up_sync(0xffffffffu, c23.z, 1);    // node 3 of the lane to the left
+    float right_x = __shfl_down_sync(0xffffffffu, c01.x, 1); // node 0 of the lane to the right
+    if (fast) {
+        if (lane == 0) left_x = __ldg(&v[l - 1].x);
+        if (lane == 31) right_x = __ldg(&v[l + 4].x);
+        // div_expr_fast, finitediff.cpp:29: (-L.x + R.x) + (-D.y + U.y)
+        float4 o;
+        o.x = __fmul_rn(__fadd_rn(__fadd_rn(-left_x, c01.z), __fadd_rn(-d01.y, u01.y)), two_dx_inv);
+        o.y = __fmul_rn(__fadd_rn(__fadd_rn(-c01.x, c23.x), __fadd_rn(-d01.w, u01.w)), two_dx_inv);
+        o.z = __fmul_rn(__fadd_rn(__fadd_rn(-c01.z, c23.z), __fadd_rn(-d23.y, u23.y)), two_dx_inv);
+        o.w = __fmul_rn(__fadd_rn(__fadd_rn(-c23.x, right_x), __fadd_rn(-d23.w, u23.w)), two_dx_inv);
+        *reinterpret_cast<float4 *>(div + l) = o;
+    } else {
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+            const int lx = lx4 + c;
+            if (lx >= g.x0 && lx < g.x1) div[(size_t)ly * g.nx + lx] = div_node(v, g, lx, ly, two_dx_inv);
+        }
+    }
+}
+
+// one node of subtract_gradient, finitediff.cpp:41-73 (v_out may alias v_in: only v[ij] itself is read)
+__device__ __forceinline__ void grad_node(float2 *v_out, const float2 *v_in, const float *__restrict__ p,
+                                          const Geo &g, int lx, int ly, float two_dx_inv)
+{
     const size_t l = (size_t)ly * g.nx + lx;
     const int gi = g.ox + lx, gj = g.oy + ly;
     const float pc = __ldg(&p[l]);
@@ -62,6 +115,63 @@ subtract_gradient_kernel(float2 *v_out, const float2 *v_in, const float *__restr
     c.x = __fsub_rn(c.x, gx);
     c.y = __fsub_rn(c.y, gy);
     v_out[l] = c;
+}
+
+// subtract_gradient, finitediff.cpp:75-82 — one node per thread (any pitch / alignment)
+__global__ void __launch_bounds__(ST_BX *ST_BY)
+subtract_gradient_kernel(float2 *v_out, const float2 *v_in, const float *__restrict__ p, Geo g,
+                         float two_dx_inv)
+{
+    const int lx = g.x0 + blockIdx.x * ST_BX + threadIdx.x;
+    const int ly = g.y0 + blockIdx.y * ST_BY + threadIdx.y;
+    if (lx >= g.x1 || ly >= g.y1) return;
+    grad_node(v_out, v_in, p, g, lx, ly, two_dx_inv);
+}
+
+// four consecutive nodes per thread (see divergence_x4_kernel)
+__global__ void __launch_bounds__(32 * X4_ROWS)
+subtract_gradient_x4_kernel(float2 *v_out, const float2 *v_in, const float *__restrict__ p, Geo g,
+                            float two_dx_inv)
+{
+    const int lane = threadIdx.x;
+    const int lx4 = (g.x0 & ~3) + 4 * (blockIdx.x * 32 + lane);
+    const int ly = g.y0 + blockIdx.y * X4_ROWS + threadIdx.y;
+    if (ly >= g.y1) return;                                  // warp-uniform
+    const size_t l = (size_t)ly * g.nx + lx4;
+    const int gi0 = g.ox + lx4, gj = g.oy + ly;
+    const bool can_load = lx4 + 3 < g.nx;
+    const bool fast = can_load && lx4 >= g.x0 && lx4 + 3 < g.x1 && gi0 > 0 && gi0 + 3 < g.GX - 1 && gj > 0 &&
+                      gj < g.GY - 1;
+    float4 pc = make_float4(0.f, 0.f, 0.f, 0.f), pd = pc, pu = pc, v01 = pc, v23 = pc;
+    if (can_load) pc = __ldg(reinterpret_cast<const float4 *>(p + l));
+    if (fast) {
+        pd = __ldg(reinterpret_cast<const float4 *>(p + l - g.nx));
+        pu = __ldg(reinterpret_cast<const float4 *>(p + l + g.nx));
+        v01 = *reinterpret_cast<const float4 *>(v_in + l);
+        v23 = *reinterpret_cast<const float4 *>(v_in + l + 2);
+    }
+    float left = __shfl_up_sync(0xffffffffu, pc.w, 1), right = __shfl_down_sync(0xffffffffu, pc.x, 1);
+    if (fast) {
+        if (lane == 0) left = __ldg(p + l - 1);
+        if (lane == 31) right = __ldg(p + l + 4);
+        // grad_sub_expr_fast, finitediff.cpp:70-72
+        v01.x = __fsub_rn(v01.x, __fmul_rn(__fsub_rn(pc.y, left), two_dx_inv));
+        v01.y = __fsub_rn(v01.y, __fmul_rn(__fsub_rn(pu.x, pd.x), two_dx_inv));
+        v01.z = __fsub_rn(v01.z, __fmul_rn(__fsub_rn(pc.z, pc.x), two_dx_inv));
+        v01.w = __fsub_rn(v01.w, __fmul_rn(__fsub_rn(pu.y, pd.y), two_dx_inv));
+        v23.x = __fsub_rn(v23.x, __fmul_rn(__fsub_rn(pc.w, pc.y), two_dx_inv));
+        v23.y = __fsub_rn(v23.y, __fmul_rn(__fsub_rn(pu.z, pd.z), two_dx_inv));
+        v23.z = __fsub_rn(v23.z, __fmul_rn(__fsub_rn(right, pc.z), two_dx_inv));
+        v23.w = __fsub_rn(v23.w, __fmul_rn(__fsub_rn(pu.w, pd.w), two_dx_inv));
+        *reinterpret_cast<float4 *>(v_out + l) = v01;
+        *reinterpret_cast<float4 *>(v_out + l + 2) = v23;
+    } else {
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+            const int lx = lx4 + c;
+            if (lx >= g.x0 && lx < g.x1) grad_node(v_out, v_in, p, g, lx, ly, two_dx_inv);
+        }
+    }
 }
 
 // Drag overwrite, ino:264-269.  The queue is drained IN ORDER and each record
@@ -110,11 +220,20 @@ static inline dim3 st_grid(const Geo &g)
     return dim3((g.x1 - g.x0 + ST_BX - 1) / ST_BX, (g.y1 - g.y0 + ST_BY - 1) / ST_BY);
 }
 
+static inline dim3 x4_grid(const Geo &g)
+{
+    const int cols = g.x1 - (g.x0 & ~3);
+    return dim3((cols + 127) / 128, (g.y1 - g.y0 + X4_ROWS - 1) / X4_ROWS);
+}
+
 int launch_divergence(const Launch &L, float *div, const float2 *v, const Geo &g, float dx)
 {
     if (g.x1 <= g.x0 || g.y1 <= g.y0) return 0;
     const float two_dx_inv = 1.0f / (2.0f * dx);  // finitediff.cpp:36, formed on the host in float
-    divergence_kernel<<<st_grid(g), dim3(ST_BX, ST_BY), 0, L.stream>>>(div, v, g, two_dx_inv);
+    if (g.nx % 4 == 0 && (uintptr_t)div % 16 == 0 && (uintptr_t)v % 16 == 0)
+        divergence_x4_kernel<<<x4_grid(g), dim3(32, X4_ROWS), 0, L.stream>>>(div, v, g, two_dx_inv);
+    else
+        divergence_kernel<<<st_grid(g), dim3(ST_BX, ST_BY), 0, L.stream>>>(div, v, g, two_dx_inv);
     ++*L.launches;
     return (int)cudaGetLastError();
 }
@@ -124,8 +243,12 @@ int launch_subtract_gradient(const Launch &L, float2 *v_out, const float2 *v_in,
 {
     if (g.x1 <= g.x0 || g.y1 <= g.y0) return 0;
     const float two_dx_inv = 1.0f / (2.0f * dx);  // finitediff.cpp:79
-    subtract_gradient_kernel<<<st_grid(g), dim3(ST_BX, ST_BY), 0, L.stream>>>(v_out, v_in, p, g,
-                                                                              two_dx_inv);
+    if (g.nx % 4 == 0 && (uintptr_t)p % 16 == 0 && (uintptr_t)v_in % 16 == 0 && (uintptr_t)v_out % 16 == 0)
+        subtract_gradient_x4_kernel<<<x4_grid(g), dim3(32, X4_ROWS), 0, L.stream>>>(v_out, v_in, p, g,
+                                                                                   two_dx_inv);
+    else
+        subtract_gradient_kernel<<<st_grid(g), dim3(ST_BX, ST_BY), 0, L.stream>>>(v_out, v_in, p, g,
+                                                                                  two_dx_inv);
     ++*L.launches;
     return (int)cudaGetLastError();
 }

@@ -65,3 +65,15 @@ def test_argument_validation_without_context(built):
     assert L.fs_ctx_destroy(None) == _lib.FS_ERR_NO_CONTEXT
     assert b"sm_100a" in L.fs_version()
     assert L.fs_error_string(_lib.FS_ERR_HALO_OVERRUN) is not None
+
+
+def test_no_contracted_packed_fma_in_sass(built):
+    """The reference's results need every multiply and add rounded separately (SURVEY.md hard part 1).
+    A single FFMA / FFMA2 in the library would mean a rounding step of the reference is skipped
+    (ptxas even contracts explicit mul.rn.f32x2 + add.rn.f32x2, so this is checked on the SASS)."""
+    import subprocess
+    import esp32_fluid_simulation_b200 as fb
+    sass = subprocess.run(["cuobjdump", "-sass", fb.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert " FFMA2 " not in sass
+    fused = [l for l in sass.splitlines() if " FFMA " in l or " FFMA." in l]
+    assert not fused, fused[:5]

@@ -95,7 +95,8 @@ def test_poisson_solve(ctx, oracle, sor_variant, shape, iters, omega, dx):
     assert_bit_equal(to_host(p), oracle.poisson_solve(d, dx, iters, omega), "pressure")
 
 
-@pytest.mark.parametrize("shape", [0, 1, 2, 3], ids=["direct-96", "direct-192", "tma-96", "tma-192"])
+@pytest.mark.parametrize("shape", [0, 1, 2, 3, 4, 5, 6],
+                         ids=["direct-96", "direct-192", "tma-96", "tma-192", "tma-144", "tma-160", "tma-192b"])
 @pytest.mark.parametrize("t_block", [1, 2, 3, 4, 6, 8])
 def test_poisson_solve_every_blocking_depth(ctx, oracle, t_block, shape):
     ctx.set_option("sor", 1)
