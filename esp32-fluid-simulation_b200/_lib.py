@@ -21,6 +21,12 @@ FS_ERR_UNSUPPORTED = -3
 FS_ERR_HALO_OVERRUN = -4
 
 
+class HaloCopy(C.Structure):
+    """fs_halo_copy: one pitched 2-D strip pushed into a neighbour's ghost region."""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("src_pitch", C.c_longlong),
+                ("dst_pitch", C.c_longlong), ("row_bytes", C.c_int), ("rows", C.c_int)]
+
+
 class Tile(C.Structure):
     """fs_tile: a rank's padded local window of a global grid."""
     _fields_ = [(n, C.c_int) for n in
@@ -77,6 +83,13 @@ def lib() -> C.CDLL:
         "fs_tile_apply_drags": ([vp, vp, I, TP, vp], I),
         "fs_tile_check": ([vp], I),
         "fs_tile_max_displacement": ([C.POINTER(I), vp, TP, f, vp], I),
+        "fs_arena_alloc": ([C.POINTER(vp), C.c_size_t, vp], I),
+        "fs_arena_free": ([vp, vp], I),
+        "fs_ipc_export": ([vp, C.c_char_p, vp], I),
+        "fs_ipc_open": ([C.POINTER(vp), C.c_char_p, vp], I),
+        "fs_ipc_close": ([vp, vp], I),
+        "fs_halo_exchange": ([C.POINTER(HaloCopy), I, C.POINTER(vp), C.POINTER(vp), I, C.c_ulonglong, vp], I),
+        "fs_ctx_set_stream": ([vp, vp], I),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the library does not export the header's symbol

@@ -21,7 +21,10 @@ struct fs_ctx {
     size_t scratch_bytes[S_COUNT];
     int *status_dev;            // device flag raised by tile advects (FS_ERR_HALO_OVERRUN)
     unsigned int *maxdisp_dev;  // max-displacement reduction cell
+    unsigned int *halo_done_dev;  // block counter of the halo-exchange kernel
     int *work_dev;              // WORK_SLOTS tile counters of the persistent SOR kernel (one per pass)
+    cudaStream_t copy_in, copy_out;   // side streams of fsh_step: PCIe copies overlap the compute
+    cudaEvent_t ev_start, ev_c_in, ev_v_done;
     size_t max_smem_optin;
     int opt_sor, opt_sor_t, opt_sor_shape, opt_advect, opt_fuse;
 };
@@ -167,20 +170,36 @@ int core_poisson_solve(fs_ctx *ctx, float *p, const float *div, const Geo &g, fl
 // there, and the projection's last operator writes back into v (out of place
 // gradient-subtract), so the reference's pointer swap (ino:255) costs no copy.
 // The dye goes c_in -> c_out.
-int core_step(fs_ctx *ctx, fs_vec2f *v, fs_vec2f *v_tmp, const fs_rgb_uq32 *c_in,
-              fs_rgb_uq32 *c_out, const fs_drag *drags, int n_drags, int dim_x, int dim_y, float dt,
-              float dx, int iters, float omega, float *p, float *div)
+int core_step_velocity(fs_ctx *ctx, fs_vec2f *v, fs_vec2f *v_tmp, const fs_drag *drags, int n_drags,
+                       const Geo &g, float dt, float dx, int iters, float omega, float *p, float *div)
 {
-    const Geo g = geo_full(dim_x, dim_y);
     int e;
     if ((e = core_advect_vec2f(ctx, v_tmp, v, v, g, dt, 1, nullptr))) return e;           // ino:253
     if (n_drags > 0 && (e = launch_apply_drags(mk(ctx), (float2 *)v_tmp, drags, n_drags, g)))
         return e;                                                                        // ino:264-269
     if ((e = launch_divergence(mk(ctx), div, (const float2 *)v_tmp, g, dx))) return e;    // ino:274
     if ((e = core_poisson_solve(ctx, p, div, g, dx, iters, omega))) return e;             // ino:275
-    if ((e = launch_subtract_gradient(mk(ctx), (float2 *)v, (const float2 *)v_tmp, p, g, dx)))
-        return e;                                                                        // ino:276
-    if ((e = core_advect_rgb(ctx, c_out, c_in, v, g, dt, 0, nullptr))) return e;          // ino:282
+    return launch_subtract_gradient(mk(ctx), (float2 *)v, (const float2 *)v_tmp, p, g, dx);  // ino:276
+}
+
+int core_step(fs_ctx *ctx, fs_vec2f *v, fs_vec2f *v_tmp, const fs_rgb_uq32 *c_in,
+              fs_rgb_uq32 *c_out, const fs_drag *drags, int n_drags, int dim_x, int dim_y, float dt,
+              float dx, int iters, float omega, float *p, float *div)
+{
+    const Geo g = geo_full(dim_x, dim_y);
+    int e;
+    if ((e = core_step_velocity(ctx, v, v_tmp, drags, n_drags, g, dt, dx, iters, omega, p, div))) return e;
+    return core_advect_rgb(ctx, c_out, c_in, v, g, dt, 0, nullptr);                       // ino:282
+}
+
+int ensure_copy_streams(fs_ctx *ctx)
+{
+    if (ctx->copy_in) return FS_OK;
+    FS_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    FS_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    FS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+    FS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_c_in, cudaEventDisableTiming));
+    FS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_v_done, cudaEventDisableTiming));
     return FS_OK;
 }
 
@@ -228,6 +247,8 @@ int fs_ctx_create(fs_ctx **out, int device, void *stream)
     cudaError_t e = cudaMalloc(&ctx->status_dev, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->maxdisp_dev, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->work_dev, WORK_SLOTS * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->halo_done_dev, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(ctx->halo_done_dev, 0, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(ctx->status_dev, 0, sizeof(int));
     if (e != cudaSuccess) {
         delete ctx;
@@ -247,6 +268,12 @@ int fs_ctx_destroy(fs_ctx *ctx)
     cudaFree(ctx->status_dev);
     cudaFree(ctx->maxdisp_dev);
     cudaFree(ctx->work_dev);
+    cudaFree(ctx->halo_done_dev);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_c_in) cudaEventDestroy(ctx->ev_c_in);
+    if (ctx->ev_v_done) cudaEventDestroy(ctx->ev_v_done);
     delete ctx;
     return FS_OK;
 }
@@ -556,17 +583,33 @@ int fsh_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags, int n_drags, int
     if ((e = ensure(ctx, S_HC2, n * sizeof(fs_rgb_uq32), &d_c2))) return e;
     if ((e = ensure(ctx, S_P, n * sizeof(float), &d_p))) return e;
     if ((e = ensure(ctx, S_DIV, n * sizeof(float), &d_div))) return e;
+    if ((e = ensure_copy_streams(ctx))) return e;
+    // The step is PCIe-bound (20 B/node each way).  Only the velocity is needed up front: the dye
+    // upload rides a side stream under the velocity phase, and the projected velocity goes home on a
+    // second side stream (the other PCIe direction) while the dye is still arriving.
+    const Geo g = geo_full(dim_x, dim_y);
+    FS_CUDA_TRY(cudaEventRecord(ctx->ev_start, ctx->stream));          // earlier work on the scratch buffers
+    FS_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_start, 0));
+    FS_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_start, 0));
     H2D(d_v, v, n * sizeof(fs_vec2f));
-    H2D(d_c, c, n * sizeof(fs_rgb_uq32));
-    if ((e = core_step(ctx, (fs_vec2f *)d_v, (fs_vec2f *)d_vtmp, (fs_rgb_uq32 *)d_c,
-                       (fs_rgb_uq32 *)d_c2, drags, n_drags, dim_x, dim_y, dt, dx, iters, omega,
-                       (float *)d_p, (float *)d_div)))
+    FS_CUDA_TRY(cudaMemcpyAsync(d_c, c, n * sizeof(fs_rgb_uq32), cudaMemcpyHostToDevice, ctx->copy_in));
+    FS_CUDA_TRY(cudaEventRecord(ctx->ev_c_in, ctx->copy_in));
+    if ((e = core_step_velocity(ctx, (fs_vec2f *)d_v, (fs_vec2f *)d_vtmp, drags, n_drags, g, dt, dx, iters,
+                                omega, (float *)d_p, (float *)d_div)))
         return e;
-    D2H(v, d_v, n * sizeof(fs_vec2f));
+    FS_CUDA_TRY(cudaEventRecord(ctx->ev_v_done, ctx->stream));
+    FS_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_v_done, 0));
+    FS_CUDA_TRY(cudaMemcpyAsync(v, d_v, n * sizeof(fs_vec2f), cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (p_out)
+        FS_CUDA_TRY(cudaMemcpyAsync(p_out, d_p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
+    if (div_out)
+        FS_CUDA_TRY(cudaMemcpyAsync(div_out, d_div, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
+    FS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_c_in, 0));
+    if ((e = core_advect_rgb(ctx, (fs_rgb_uq32 *)d_c2, (fs_rgb_uq32 *)d_c, (fs_vec2f *)d_v, g, dt, 0, nullptr)))
+        return e;
     D2H(c, d_c2, n * sizeof(fs_rgb_uq32));
-    if (p_out) D2H(p_out, d_p, n * sizeof(float));
-    if (div_out) D2H(div_out, d_div, n * sizeof(float));
     FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    FS_CUDA_TRY(cudaStreamSynchronize(ctx->copy_out));
     return FS_OK;
 }
 
@@ -702,6 +745,97 @@ int fs_tile_max_displacement(int *out_nodes, const fs_vec2f *vel, const fs_tile 
     long long nodes = (long long)d + 2;
     *out_nodes = nodes > 0x3fffffff ? 0x3fffffff : (int)nodes;
     return FS_OK;
+}
+
+// ---- halo exchange over peer memory ------------------------------------------------------------
+
+int fs_ctx_set_stream(fs_ctx *ctx, void *stream)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    ctx->stream = (cudaStream_t)stream;
+    return FS_OK;
+}
+
+int fs_arena_alloc(void **out, size_t bytes, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!out || bytes == 0) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    FS_CUDA_TRY(cudaMalloc(out, bytes));   // cudaMalloc (not a pool): exportable through CUDA IPC
+    FS_CUDA_TRY(cudaMemset(*out, 0, bytes));
+    return FS_OK;
+}
+
+int fs_arena_free(void *arena, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    DeviceGuard guard(ctx->device);
+    FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    FS_CUDA_TRY(cudaFree(arena));
+    return FS_OK;
+}
+
+int fs_ipc_export(void *arena, unsigned char handle[64], fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!arena || !handle) return FS_ERR_INVALID_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    DeviceGuard guard(ctx->device);
+    cudaIpcMemHandle_t h;
+    FS_CUDA_TRY(cudaIpcGetMemHandle(&h, arena));
+    memcpy(handle, &h, 64);
+    return FS_OK;
+}
+
+int fs_ipc_open(void **peer_arena, const unsigned char handle[64], fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!peer_arena || !handle) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    FS_CUDA_TRY(cudaIpcOpenMemHandle(peer_arena, h, cudaIpcMemLazyEnablePeerAccess));
+    return FS_OK;
+}
+
+int fs_ipc_close(void *peer_arena, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    DeviceGuard guard(ctx->device);
+    FS_CUDA_TRY(cudaIpcCloseMemHandle(peer_arena));
+    return FS_OK;
+}
+
+int fs_halo_exchange(const fs_halo_copy *copies, int n_copies, void *const *signal_flags,
+                     void *const *wait_flags, int n_peers, unsigned long long seq, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (n_copies < 0 || n_copies > FS_HALO_MAX_COPIES || n_peers < 0 || n_peers > FS_HALO_MAX_PEERS ||
+        (n_copies > 0 && !copies) || (n_peers > 0 && (!signal_flags || !wait_flags)))
+        return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    HaloArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int c = 0; c < n_copies; c++) {
+        const fs_halo_copy &s = copies[c];
+        if (!s.src || !s.dst || s.row_bytes < 0 || s.rows < 0 || (s.row_bytes & 3) || (s.src_pitch & 3) ||
+            (s.dst_pitch & 3) || ((uintptr_t)s.src & 3) || ((uintptr_t)s.dst & 3))
+            return FS_ERR_INVALID_ARG;
+        a.copies[c].src = (const uint32_t *)s.src;
+        a.copies[c].dst = (uint32_t *)s.dst;
+        a.copies[c].src_pitch_words = (int)(s.src_pitch / 4);
+        a.copies[c].dst_pitch_words = (int)(s.dst_pitch / 4);
+        a.copies[c].row_words = s.row_bytes / 4;
+        a.copies[c].rows = s.rows;
+    }
+    for (int k = 0; k < n_peers; k++) {
+        a.signal[k] = (unsigned long long *)signal_flags[k];
+        a.wait[k] = (unsigned long long *)wait_flags[k];
+    }
+    a.seq = seq;
+    a.n_copies = n_copies;
+    a.n_peers = n_peers;
+    return launch_halo_exchange(mk(ctx), a, ctx->halo_done_dev);
 }
 
 }  // extern "C"

@@ -53,6 +53,23 @@ int launch_ensemble(const Launch &L, float2 *v, uint32_t *c, const fs_drag *drag
                     const int *counts_dev, int max_drags, int batch, int dim_x, int dim_y, float dt,
                     float dx, int iters, float omega, int n_steps);
 
+// halo.cu — one-kernel halo exchange over peer (NVLink) memory
+constexpr int HALO_MAX_COPIES = 32, HALO_MAX_PEERS = 8;
+struct HaloCopy {
+    const uint32_t *src;      // this rank's window
+    uint32_t *dst;            // a neighbour's ghost region (peer pointer)
+    int src_pitch_words, dst_pitch_words, row_words, rows;
+};
+struct HaloArgs {
+    HaloCopy copies[HALO_MAX_COPIES];
+    int block_end[HALO_MAX_COPIES];           // filled by the launcher
+    unsigned long long *signal[HALO_MAX_PEERS];  // the neighbours' flag slots for this rank
+    unsigned long long *wait[HALO_MAX_PEERS];    // this rank's flag slots, one per neighbour
+    unsigned long long seq;
+    int n_copies, n_peers;
+};
+int launch_halo_exchange(const Launch &L, HaloArgs &a, unsigned int *done_counter);
+
 // upscale.cu — ino:116-177
 int launch_upscale4_rgb565(const Launch &L, uint16_t *out, const uint32_t *c, int dim_x, int dim_y);
 

@@ -25,7 +25,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Tile, check
+from ._lib import HaloCopy, Tile, check
 
 DRAG_DTYPE = np.dtype([("cx", "<u2"), ("cy", "<u2"), ("vx", "<f4"), ("vy", "<f4")])  # ino:45-48
 
@@ -251,6 +251,41 @@ class Context:
         check(self._L.fs_tile_max_displacement(C.byref(out), _ptr(vel, "float32")[0], C.byref(tile),
                                                dt, self._h), "fs_tile_max_displacement")
         return out.value
+
+
+    # --- halo exchange over NVLink peer memory ---------------------------------------------------
+    def arena_alloc(self, nbytes: int) -> int:
+        out = C.c_void_p()
+        check(self._L.fs_arena_alloc(C.byref(out), nbytes, self._h), "fs_arena_alloc")
+        return out.value
+
+    def arena_free(self, ptr: int):
+        check(self._L.fs_arena_free(C.c_void_p(ptr), self._h), "fs_arena_free")
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(self._L.fs_ipc_export(C.c_void_p(ptr), buf, self._h), "fs_ipc_export")
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        out = C.c_void_p()
+        check(self._L.fs_ipc_open(C.byref(out), C.create_string_buffer(handle, 64), self._h), "fs_ipc_open")
+        return out.value
+
+    def ipc_close(self, ptr: int):
+        check(self._L.fs_ipc_close(C.c_void_p(ptr), self._h), "fs_ipc_close")
+
+    def halo_exchange(self, copies, signal_flags, wait_flags, seq: int):
+        """copies: [(src, dst, src_pitch, dst_pitch, row_bytes, rows)], flags: lists of addresses."""
+        n, k = len(copies), len(signal_flags)
+        arr = (HaloCopy * max(n, 1))(*[HaloCopy(*c) for c in copies])
+        sig = (C.c_void_p * max(k, 1))(*signal_flags)
+        wai = (C.c_void_p * max(k, 1))(*wait_flags)
+        check(self._L.fs_halo_exchange(arr, n, sig, wai, k, seq, self._h), "fs_halo_exchange")
+
+    def set_stream(self, stream):
+        s = getattr(stream, "cuda_stream", stream) or 0
+        check(self._L.fs_ctx_set_stream(self._h, C.c_void_p(s)), "fs_ctx_set_stream")
 
 
 # ---- module-level functions with the reference's exact names -------------------------

@@ -180,6 +180,34 @@ int fs_tile_check(fs_ctx *ctx);
 int fs_tile_max_displacement(int *out_nodes, const fs_vec2f *vel, const fs_tile *t,
                              float dt, fs_ctx *ctx);
 
+/* ---- halo exchange over NVLink peer memory (no NCCL on the critical path) -------- */
+/* Field windows that take part in exchanges live in an arena from fs_arena_alloc
+ * (plain cudaMalloc, zero-filled; its first bytes are the caller's flag slots).  A
+ * rank exports its arena with fs_ipc_export, ships the 64-byte handle to its
+ * neighbours by any means (torch.distributed), and they map it with fs_ipc_open. */
+int fs_arena_alloc(void **out, size_t bytes, fs_ctx *ctx);
+int fs_arena_free(void *arena, fs_ctx *ctx);
+int fs_ipc_export(void *arena, unsigned char handle[64], fs_ctx *ctx);
+int fs_ipc_open(void **peer_arena, const unsigned char handle[64], fs_ctx *ctx);
+int fs_ipc_close(void *peer_arena, fs_ctx *ctx);
+
+#define FS_HALO_MAX_COPIES 32
+#define FS_HALO_MAX_PEERS 8
+typedef struct fs_halo_copy {       /* one pitched 2-D strip, sizes in bytes (multiples of 4) */
+    const void *src;                /* in this rank's window */
+    void *dst;                      /* in a neighbour's ghost region (pointer into its mapped arena) */
+    long long src_pitch, dst_pitch;
+    int row_bytes, rows;
+} fs_halo_copy;
+/* ONE kernel: store the strips into the neighbours' ghosts, then write `seq` to each
+ * signal_flags[k] (a uint64 slot in neighbour k's arena) and wait until every
+ * wait_flags[k] (uint64 slots in this rank's arena) holds a value >= seq.  `seq` must
+ * grow by one per exchange, identically on all ranks. */
+int fs_halo_exchange(const fs_halo_copy *copies, int n_copies, void *const *signal_flags,
+                     void *const *wait_flags, int n_peers, unsigned long long seq, fs_ctx *ctx);
+/* Re-target the context at another stream (e.g. a capturing stream). */
+int fs_ctx_set_stream(fs_ctx *ctx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
