@@ -174,7 +174,7 @@ def run_b200_arm(args):
 
     if world > 1:
         from esp32_fluid_simulation_b200 import dist as fdist
-        result = fdist.bench_decomposed(args, GRID, ITERS, N_DRAGS)
+        result = fdist.bench_decomposed(args, GRID, args.iters, N_DRAGS)
     else:
         result = bench_single(args, fb, synth, torch)
     if rank == 0:
@@ -302,6 +302,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--global-grid", default="", help="N>1 only: GXxGY global grid instead of 4096^2 per GPU "
+                    "(BASELINE.json configs[3] = 16384x16384, configs[4] = 24576x32768)")
+    ap.add_argument("--iters", type=int, default=ITERS, help="SOR iterations per step (N>1 extra configs)")
+    ap.add_argument("--upscale", action="store_true", help="N>1: also produce the 4x RGB565 frame every step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

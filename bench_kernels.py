@@ -100,7 +100,7 @@ def main():
                 run_sor(f"[blocked shape={shape} T={t}]")
         ctx.set_option("sor_shape", 3)
         ctx.set_option("sor_t", 8)
-        for fuse in (0, 1):
+        for fuse in (0, 1, 2, 3):
             ctx.set_option("fuse", fuse)
             run_step(f"[fuse={fuse}]")
     else:

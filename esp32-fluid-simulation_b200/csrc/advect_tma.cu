@@ -20,6 +20,7 @@
 // lines; velocity (8 B) is stored directly, coalesced.
 #include "advect.cuh"
 #include "kernels.h"
+#include "stencil.cuh"
 #include "tma.cuh"
 
 namespace fs {
@@ -38,8 +39,9 @@ struct TileShape {
 };
 
 // Fetch a source node: shared-memory tile if staged, else global (L2) gather.
-template <class P>
+template <class P, int W = TileShape<P>::W, int H = TileShape<P>::H>
 struct TileFetch {
+    static constexpr int ROW_WORDS = W * P::NC;
     const typename P::raw_t *tile;   // smem, ROW_WORDS words per row
     const typename P::raw_t *base;   // global window
     int bx0, by0;                    // local coordinate of the tile's first staged node
@@ -55,8 +57,8 @@ struct TileFetch {
             return;
         }
         const int tx = lx - bx0, ty = ly - by0;
-        if ((unsigned)tx < (unsigned)TileShape<P>::W && (unsigned)ty < (unsigned)TileShape<P>::H) {
-            const typename P::raw_t *q = tile + ty * TileShape<P>::ROW_WORDS + tx * P::NC;
+        if ((unsigned)tx < (unsigned)W && (unsigned)ty < (unsigned)H) {
+            const typename P::raw_t *q = tile + ty * ROW_WORDS + tx * P::NC;
             if constexpr (P::NC == 2) {
                 const float2 t = *reinterpret_cast<const float2 *>(q);
                 o[0] = t.x;
@@ -76,9 +78,9 @@ struct TileFetch {
 // The general `sample` (walls, corners, backtraces that leave the staged tile) is kept out of line:
 // the unrolled per-row loop then only carries the short interior path, and the kernel stays inside
 // the instruction cache (ncu: `no_instruction` was the top stall with it inlined 8 times).
-template <class P>
-__device__ __noinline__ void sample_slow(typename P::raw_t (&out)[P::NC], const TileFetch<P> &fetch, float si,
-                                         float sj, int GX, int GY, bool no_slip)
+template <class P, class F>
+__device__ __noinline__ void sample_slow(typename P::raw_t (&out)[P::NC], const F &fetch, float si, float sj,
+                                         int GX, int GY, bool no_slip)
 {
     sample<P>(out, fetch, si, sj, GX, GY, no_slip);
 }
@@ -93,6 +95,12 @@ struct TmaAdvectArgs {
     int vel_is_p;        // velocity advect: the velocity of a node is already in the staged tile
     int store_tma;       // dye: write the tile with a bulk-tensor store
     int *status;
+    // fused gradient-subtract (fs_step, ino:276+282): when grad_p is set, `vel` holds the UNPROJECTED
+    // velocity; each thread forms v - grad p for its node, stores it to v_out and advects with it
+    // (the dye backtrace only needs the projected velocity at the node itself).
+    const float *grad_p;
+    float2 *v_out;
+    float two_dx_inv;
 };
 
 template <class P>
@@ -129,7 +137,12 @@ advect_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
 #pragma unroll
         for (int it = 0; it < ITERS; it++) {
             const int lx = tx0 + cx, ly = ty0 + cy + it * ROWS_PER_IT;
-            vel[it] = (lx < g.x1 && ly < g.y1) ? __ldg(a.vel + (size_t)ly * g.nx + lx) : make_float2(0.f, 0.f);
+            const bool live = lx < g.x1 && ly < g.y1;
+            vel[it] = live ? __ldg(a.vel + (size_t)ly * g.nx + lx) : make_float2(0.f, 0.f);
+            if (a.grad_p && live) {
+                vel[it] = grad_sub_value(vel[it], a.grad_p, g, lx, ly, a.two_dx_inv);
+                a.v_out[(size_t)ly * g.nx + lx] = vel[it];
+            }
         }
     }
     mbar_wait(&bar, 0);
@@ -213,19 +226,141 @@ advect_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     }
 }
 
+// ---- fused: advect velocity (no-slip) + drag overwrite + divergence (ino:253, 264-269, 274) -------------
+// The CTA advects its 64x32 tile PLUS a one-node ring into shared memory, applies the drag records
+// that land there (in queue order, later wins), then forms the divergence of the tile from shared
+// memory and writes both the forced velocity and the divergence.  Saves the divergence kernel's
+// read of the velocity (8 of its 12 B/node) and two launches; the ring costs 9 % more backtraces.
+constexpr int AD_LEFT = AT_HALO + 2;   // ring + halo, rounded up so the box starts on a 16-byte boundary (TMA)
+constexpr int AD_W = ((AD_LEFT + AT_TX + 1 + AT_HALO + 1 + 1) / 2) * 2;   // staged source tile (nodes)
+constexpr int AD_H = AT_TY + 2 + 2 * AT_HALO + 1;
+constexpr int AD_AW = AT_TX + 2, AD_AH = AT_TY + 2;               // advected tile + ring
+constexpr int AD_MAX_DRAGS = 128;
+
+struct AdvDivArgs {
+    float2 *v_out;
+    const float2 *v_in;
+    float *div;
+    Geo g;
+    float dt, two_dx_inv;
+    int n_drags;
+    fs_drag drags[AD_MAX_DRAGS];
+};
+
+__global__ void __launch_bounds__(AT_THREADS)
+advect_div_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ AdvDivArgs a)
+{
+    using P = Vec2Payload;
+    constexpr int ROW_WORDS = AD_W * 2;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float *tile = reinterpret_cast<float *>(smem);
+    float2 *adv = reinterpret_cast<float2 *>(smem + ((ROW_WORDS * AD_H * 4 + 127) & ~127));
+    __shared__ __align__(8) uint64_t bar;
+
+    const Geo &g = a.g;
+    const int tx0 = g.x0 + blockIdx.x * AT_TX, ty0 = g.y0 + blockIdx.y * AT_TY;
+    const int bx0 = tx0 - AD_LEFT, by0 = ty0 - 1 - AT_HALO;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, ROW_WORDS * AD_H * 4);
+        tma_load_2d(tile, &in_map, bx0 * 2, by0, &bar);
+    }
+    TileFetch<P, AD_W, AD_H> fetch{tile, reinterpret_cast<const float *>(a.v_in), bx0, by0, g.ox, g.oy, g.nx, g.ny,
+                                   nullptr};
+    const int tx_lo = max(0, -bx0), tx_hi = min(AD_W - 1, g.nx - 1 - bx0);
+    const int ty_lo = max(0, -by0), ty_hi = min(AD_H - 1, g.ny - 1 - by0);
+    const float x_max = (float)(g.GX - 1), y_max = (float)(g.GY - 1);
+    mbar_wait(&bar, 0);
+
+    // ---- advect tile + ring into shared memory ----
+#pragma unroll 1
+    for (int k = threadIdx.x; k < AD_AW * AD_AH; k += AT_THREADS) {
+        const int ay = k / AD_AW, ax = k - ay * AD_AW;
+        const int lx = tx0 - 1 + ax, ly = ty0 - 1 + ay;
+        float out[2] = {0.f, 0.f};
+        if (lx >= 0 && lx < g.nx && ly >= 0 && ly < g.ny) {
+            const float2 vv = *reinterpret_cast<const float2 *>(tile + (ay + AT_HALO) * ROW_WORDS + (ax + AD_LEFT - 1) * 2);
+            float si, sj;
+            backtrace(si, sj, g.ox + lx, g.oy + ly, vv, a.dt);
+            const float fi = floorf(si), fj = floorf(sj);
+            const int tx = (int)fi - g.ox - bx0, ty = (int)fj - g.oy - by0;
+            const bool interior = si >= 0.0f && si < x_max && sj >= 0.0f && sj < y_max;
+            if (interior && tx >= tx_lo && tx < tx_hi && ty >= ty_lo && ty < ty_hi) {
+                const float di = __fsub_rn(si, fi), dj = __fsub_rn(sj, fj);
+                const float wi = __fsub_rn(1.0f, di), wj = __fsub_rn(1.0f, dj);
+                const float *q = tile + ty * ROW_WORDS + tx * 2;
+                const float2 p11 = *reinterpret_cast<const float2 *>(q);
+                const float2 p21 = *reinterpret_cast<const float2 *>(q + 2);
+                const float2 p12 = *reinterpret_cast<const float2 *>(q + ROW_WORDS);
+                const float2 p22 = *reinterpret_cast<const float2 *>(q + ROW_WORDS + 2);
+                out[0] = mixf(wi, di, mixf(wj, dj, p11.x, p12.x), mixf(wj, dj, p21.x, p22.x));
+                out[1] = mixf(wi, di, mixf(wj, dj, p11.y, p12.y), mixf(wj, dj, p21.y, p22.y));
+            } else {
+                sample_slow<P>(out, fetch, si, sj, g.GX, g.GY, true);
+            }
+        }
+        adv[k] = make_float2(out[0], out[1]);
+    }
+    __syncthreads();
+
+    // ---- drag overwrite (ino:264-269) on the tile + ring: parallel hit test, in-order replay ----
+    if (a.n_drags > 0) {
+        int hit = 0;
+        for (int k = threadIdx.x; k < a.n_drags; k += AT_THREADS) {
+            const int lx = (int)a.drags[k].cy - g.ox, ly = (int)a.drags[k].cx - g.oy;
+            hit |= (lx >= tx0 - 1 && lx <= tx0 + AT_TX && ly >= ty0 - 1 && ly <= ty0 + AT_TY);
+        }
+        if (__syncthreads_or(hit)) {
+            if (threadIdx.x == 0) {
+                for (int k = 0; k < a.n_drags; k++) {
+                    const fs_drag m = a.drags[k];
+                    if (m.cy >= g.GX || m.cx >= g.GY) continue;
+                    const int ax = (int)m.cy - g.ox - (tx0 - 1), ay = (int)m.cx - g.oy - (ty0 - 1);
+                    if (ax >= 0 && ax < AD_AW && ay >= 0 && ay < AD_AH) adv[ay * AD_AW + ax] = make_float2(m.vy, m.vx);
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- forced velocity + its divergence for the tile ----
+    constexpr int ROWS_PER_IT = AT_THREADS / AT_TX, ITERS = AT_TY / ROWS_PER_IT;
+    const int cx = threadIdx.x % AT_TX, cy = threadIdx.x / AT_TX;
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {
+        const int ry = cy + it * ROWS_PER_IT;
+        const int lx = tx0 + cx, ly = ty0 + ry;
+        if (lx >= g.x1 || ly >= g.y1) continue;
+        const float2 c = adv[(ry + 1) * AD_AW + cx + 1];
+        const float d = div_value(c, adv[(ry + 1) * AD_AW + cx].x, adv[(ry + 1) * AD_AW + cx + 2].x,
+                                  adv[ry * AD_AW + cx + 1].y, adv[(ry + 2) * AD_AW + cx + 1].y, g.ox + lx, g.oy + ly,
+                                  g.GX, g.GY, a.two_dx_inv);
+        const size_t l = (size_t)ly * g.nx + lx;
+        a.v_out[l] = c;
+        a.div[l] = d;
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------
 
 template <class P>
 bool advect_tma_legal(const void *p, const Geo &g)
 {
-    // TMA: 16-byte aligned base and row pitch; boxes of at most 256 words
-    return ((uintptr_t)p % 16 == 0) && (((size_t)g.nx * P::NC * 4) % 16 == 0) && g.nx >= AT_TX && g.ny >= AT_TY &&
+    // TMA: 16-byte aligned base, row pitch AND box start (tile origin - halo = x0 - 4 + 64k nodes);
+    // boxes of at most 256 words
+    return ((uintptr_t)p % 16 == 0) && (((size_t)g.nx * P::NC * 4) % 16 == 0) && (g.x0 % 4 == 0) &&
+           g.nx >= AT_TX && g.ny >= AT_TY &&
            tma_encode_fn() != nullptr;
 }
 
 template <class P>
 static int launch_tma(const Launch &L, void *next_p, const void *p, const float2 *vel, const Geo &g, float dt,
-                      bool no_slip, int *status)
+                      bool no_slip, int *status, const float *grad_p = nullptr, float2 *v_out = nullptr,
+                      float two_dx_inv = 0.0f)
 {
     using TS = TileShape<P>;
     const int w = g.x1 - g.x0, h = g.y1 - g.y0;
@@ -237,6 +372,9 @@ static int launch_tma(const Launch &L, void *next_p, const void *p, const float2
     a.next_p = next_p; a.p = p; a.vel = vel; a.g = g; a.dt = dt; a.no_slip = no_slip ? 1 : 0;
     a.vel_is_p = (P::NC == 2 && (const void *)vel == p) ? 1 : 0;
     a.status = status;
+    a.grad_p = grad_p;
+    a.v_out = v_out;
+    a.two_dx_inv = two_dx_inv;
     a.store_tma = 0;
     out_map = in_map;
     if (P::NC == 3) {
@@ -269,6 +407,41 @@ int launch_advect_rgb_tma(const Launch &L, uint32_t *next_c, const uint32_t *c, 
                           float dt, bool no_slip, int *status)
 {
     return launch_tma<RgbPayload>(L, next_c, c, vel, g, dt, no_slip, status);
+}
+
+int launch_advect_div_tma(const Launch &L, float2 *v_out, const float2 *v_in, float *div, const fs_drag *drags_host,
+                          int n_drags, const Geo &g, float dt, float dx)
+{
+    const int w = g.x1 - g.x0, h = g.y1 - g.y0;
+    if (w <= 0 || h <= 0) return 0;
+    if (n_drags > AD_MAX_DRAGS) return (int)cudaErrorInvalidValue;
+    CUtensorMap in_map;
+    if (!tma_make_map_2d(&in_map, v_in, (uint64_t)g.nx * 2, g.ny, (uint64_t)g.nx * 2, AD_W * 2, AD_H))
+        return (int)cudaErrorInvalidValue;
+    AdvDivArgs a;
+    a.v_out = v_out; a.v_in = v_in; a.div = div; a.g = g; a.dt = dt;
+    a.two_dx_inv = 1.0f / (2.0f * dx);
+    a.n_drags = n_drags;
+    for (int k = 0; k < n_drags; k++) a.drags[k] = drags_host[k];
+    const size_t smem = ((AD_W * 2 * AD_H * 4 + 127) & ~127) + AD_AW * AD_AH * 8;
+    cudaError_t e = cudaFuncSetAttribute(advect_div_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((w + AT_TX - 1) / AT_TX, (h + AT_TY - 1) / AT_TY);
+    advect_div_tma_kernel<<<grid, AT_THREADS, smem, L.stream>>>(in_map, a);
+    ++*L.launches;
+    return (int)cudaGetLastError();
+}
+
+int advect_div_max_drags() { return AD_MAX_DRAGS; }
+
+// dye advect with the gradient-subtract of the projection folded in: v_out = v_tmp - grad p, and the
+// dye is advected with v_out (ino:276 + ino:282 in one pass over the grid)
+int launch_advect_rgb_tma_grad(const Launch &L, uint32_t *next_c, const uint32_t *c, float2 *v_out,
+                               const float2 *v_tmp, const float *p, const Geo &g, float dt, float dx,
+                               bool no_slip, int *status)
+{
+    return launch_tma<RgbPayload>(L, next_c, c, v_tmp, g, dt, no_slip, status, p, v_out, 1.0f / (2.0f * dx));
 }
 
 }  // namespace fs

@@ -2,6 +2,7 @@
 // orchestration.  No arithmetic of the sim lives here — only which kernels run
 // in which order on which buffers.
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <new>
 
@@ -21,6 +22,7 @@ struct fs_ctx {
     size_t scratch_bytes[S_COUNT];
     int *status_dev;            // device flag raised by tile advects (FS_ERR_HALO_OVERRUN)
     unsigned int *maxdisp_dev;  // max-displacement reduction cell
+    double *resid_dev;            // residual reduction cells: [0] sum of squares, then max bits
     unsigned int *halo_done_dev;  // block counter of the halo-exchange kernel
     int *work_dev;              // WORK_SLOTS tile counters of the persistent SOR kernel (one per pass)
     cudaStream_t copy_in, copy_out;   // side streams of fsh_step: PCIe copies overlap the compute
@@ -171,14 +173,25 @@ int core_poisson_solve(fs_ctx *ctx, float *p, const float *div, const Geo &g, fl
 // gradient-subtract), so the reference's pointer swap (ino:255) costs no copy.
 // The dye goes c_in -> c_out.
 int core_step_velocity(fs_ctx *ctx, fs_vec2f *v, fs_vec2f *v_tmp, const fs_drag *drags, int n_drags,
-                       const Geo &g, float dt, float dx, int iters, float omega, float *p, float *div)
+                       const Geo &g, float dt, float dx, int iters, float omega, float *p, float *div,
+                       bool with_gradient = true)
 {
     int e;
-    if ((e = core_advect_vec2f(ctx, v_tmp, v, v, g, dt, 1, nullptr))) return e;           // ino:253
-    if (n_drags > 0 && (e = launch_apply_drags(mk(ctx), (float2 *)v_tmp, drags, n_drags, g)))
-        return e;                                                                        // ino:264-269
-    if ((e = launch_divergence(mk(ctx), div, (const float2 *)v_tmp, g, dx))) return e;    // ino:274
+    const bool whole = g.ox == 0 && g.oy == 0 && g.x0 == 0 && g.y0 == 0 && g.x1 == g.nx && g.y1 == g.ny &&
+                       g.nx == g.GX && g.ny == g.GY;
+    if ((ctx->opt_fuse & 1) && ctx->opt_advect == 1 && whole && n_drags <= advect_div_max_drags() &&
+        advect_vec2f_tma_legal((const float2 *)v, g)) {
+        // ino:253 + 264-269 + 274 in one pass over the grid
+        if ((e = launch_advect_div_tma(mk(ctx), (float2 *)v_tmp, (const float2 *)v, div, drags, n_drags, g, dt, dx)))
+            return e;
+    } else {
+        if ((e = core_advect_vec2f(ctx, v_tmp, v, v, g, dt, 1, nullptr))) return e;           // ino:253
+        if (n_drags > 0 && (e = launch_apply_drags(mk(ctx), (float2 *)v_tmp, drags, n_drags, g)))
+            return e;                                                                        // ino:264-269
+        if ((e = launch_divergence(mk(ctx), div, (const float2 *)v_tmp, g, dx))) return e;    // ino:274
+    }
     if ((e = core_poisson_solve(ctx, p, div, g, dx, iters, omega))) return e;             // ino:275
+    if (!with_gradient) return FS_OK;   // folded into the dye advect by the caller
     return launch_subtract_gradient(mk(ctx), (float2 *)v, (const float2 *)v_tmp, p, g, dx);  // ino:276
 }
 
@@ -188,7 +201,12 @@ int core_step(fs_ctx *ctx, fs_vec2f *v, fs_vec2f *v_tmp, const fs_rgb_uq32 *c_in
 {
     const Geo g = geo_full(dim_x, dim_y);
     int e;
-    if ((e = core_step_velocity(ctx, v, v_tmp, drags, n_drags, g, dt, dx, iters, omega, p, div))) return e;
+    const bool fuse_grad = (ctx->opt_fuse & 2) && ctx->opt_advect == 1 && advect_rgb_tma_legal((const uint32_t *)c_in, g);
+    if ((e = core_step_velocity(ctx, v, v_tmp, drags, n_drags, g, dt, dx, iters, omega, p, div, !fuse_grad)))
+        return e;
+    if (fuse_grad)   // ino:276 + ino:282 in one pass: v = v_tmp - grad p, dye advected with v
+        return launch_advect_rgb_tma_grad(mk(ctx), (uint32_t *)c_out, (const uint32_t *)c_in, (float2 *)v,
+                                          (const float2 *)v_tmp, p, g, dt, dx, false, nullptr);
     return core_advect_rgb(ctx, c_out, c_in, v, g, dt, 0, nullptr);                       // ino:282
 }
 
@@ -247,6 +265,7 @@ int fs_ctx_create(fs_ctx **out, int device, void *stream)
     cudaError_t e = cudaMalloc(&ctx->status_dev, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->maxdisp_dev, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->work_dev, WORK_SLOTS * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->resid_dev, 2 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->halo_done_dev, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(ctx->halo_done_dev, 0, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(ctx->status_dev, 0, sizeof(int));
@@ -269,6 +288,7 @@ int fs_ctx_destroy(fs_ctx *ctx)
     cudaFree(ctx->maxdisp_dev);
     cudaFree(ctx->work_dev);
     cudaFree(ctx->halo_done_dev);
+    cudaFree(ctx->resid_dev);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
@@ -387,6 +407,23 @@ int fs_sor_half_sweep(float *p, const float *div, int dim_x, int dim_y, float dx
     if (!p || !div || p == div || bad_dims(dim_x, dim_y)) return FS_ERR_INVALID_ARG;
     DeviceGuard guard(ctx->device);
     return launch_sor_half_sweep(mk(ctx), p, div, geo_full(dim_x, dim_y), dx, omega, parity);
+}
+
+int fs_poisson_residual(float *max_abs, double *l2, const float *p, const float *div, int dim_x, int dim_y,
+                        float dx, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!p || !div || bad_dims(dim_x, dim_y) || (!max_abs && !l2)) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    unsigned int *max_bits = (unsigned int *)(ctx->resid_dev + 1);
+    int e = launch_sor_residual(mk(ctx), p, div, geo_full(dim_x, dim_y), dx, max_bits, ctx->resid_dev);
+    if (e) return e;
+    double host[2];
+    FS_CUDA_TRY(cudaMemcpyAsync(host, ctx->resid_dev, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
+    FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (l2) *l2 = sqrt(host[0]);
+    if (max_abs) memcpy(max_abs, &host[1], sizeof(float));
+    return FS_OK;
 }
 
 int fs_apply_drags(fs_vec2f *v, const fs_drag *drags, int n, int dim_x, int dim_y, fs_ctx *ctx)

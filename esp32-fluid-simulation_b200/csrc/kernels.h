@@ -28,6 +28,14 @@ int launch_advect_vec2f_tma(const Launch &L, float2 *next_p, const float2 *p, co
 int launch_advect_rgb_tma(const Launch &L, uint32_t *next_c, const uint32_t *c, const float2 *vel,
                           const Geo &g, float dt, bool no_slip, int *status);
 
+// fused advect velocity (no-slip) + drags + divergence over a WHOLE grid (g must be geo_full)
+int launch_advect_div_tma(const Launch &L, float2 *v_out, const float2 *v_in, float *div, const fs_drag *drags_host,
+                          int n_drags, const Geo &g, float dt, float dx);
+int advect_div_max_drags();
+int launch_advect_rgb_tma_grad(const Launch &L, uint32_t *next_c, const uint32_t *c, float2 *v_out,
+                               const float2 *v_tmp, const float *p, const Geo &g, float dt, float dx,
+                               bool no_slip, int *status);
+
 // stencil.cu — finitediff.cpp:9-82, ino:264-269
 int launch_divergence(const Launch &L, float *div, const float2 *v, const Geo &g, float dx);
 int launch_subtract_gradient(const Launch &L, float2 *v_out, const float2 *v_in, const float *p,
@@ -38,6 +46,9 @@ int launch_max_displacement(const Launch &L, unsigned int *out_bits, const float
 // sor.cu — poisson.cpp:14-125
 int launch_sor_half_sweep(const Launch &L, float *p, const float *div, const Geo &g, float dx,
                           float omega, int parity);
+
+int launch_sor_residual(const Launch &L, const float *p, const float *div, const Geo &g, float dx,
+                        unsigned int *out_max_bits, double *out_sumsq);
 
 // sor_blocked.cu — `n_half` colour half-sweeps per HBM round trip, p_in -> p_out (distinct
 // buffers; p_in == nullptr means all zero).  shape 0 = 128x96 region, 2 CTAs/SM; 1 = 128x192, 1 CTA/SM;

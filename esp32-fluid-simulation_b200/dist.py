@@ -450,6 +450,10 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     px, py = process_grid(world)
     gx, gy = tile_edge * px, tile_edge * py
+    scaling = "weak"
+    if getattr(args, "global_grid", ""):
+        gx, gy = (int(t) for t in args.global_grid.lower().split("x"))
+        scaling = "strong"
     dev = torch.device("cuda", local_rank)
     ghost = 64
     mode = os.environ.get("FS_HALO", "peer")        # peer = NVLink stores (default), nccl = send/recv
@@ -468,8 +472,18 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
     sim.load(synth.velocity(gx, gy, window=(w.ox, w.oy, w.nx, w.ny)),
              synth.dye(gx, gy, window=(w.ox, w.oy, w.nx, w.ny)))
     drags = [synth.drags(gx, gy, s, n=n_drags) for s in range(args.warmup + args.steps)]
+    frame = None
+    if getattr(args, "upscale", False):
+        # the rank's part of the 4x RGB565 frame (ino:116-177): upscale the window, ghosts included
+        frame = torch.empty((w.nx - 1) * 4, (w.ny - 1) * 4, dtype=torch.int16, device=dev)
+
+    def one_step(k):
+        sim.step(drags[k])
+        if frame is not None:
+            ops.ctx.upscale4_rgb565(frame, sim.c, w.nx, w.ny)
+
     for s in range(args.warmup):
-        sim.step(drags[s])
+        one_step(s)
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
@@ -478,7 +492,7 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
     t0 = time.perf_counter()
     e0.record()
     for s in range(args.warmup, args.warmup + args.steps):
-        sim.step(drags[s])
+        one_step(s)
     e1.record()
     torch.cuda.synchronize()
     if static_halo is not None:
@@ -494,10 +508,11 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
     return {
         "metric": "Mcell-steps/s (advect+project, 50 SOR iters) at 4096^2", "value": value,
         "unit": "Mcell-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32+uq32", "data": "synthetic",
-        "config": {"workload": f"{gx}x{gy} grid block-decomposed {px}x{py}, {tile_edge}x{tile_edge} nodes per GPU, "
-                               f"{iters} SOR iterations, velocity + dye advection",
+        "config": {"workload": f"{gx}x{gy} grid block-decomposed {px}x{py}, {w.x1 - w.x0}x{w.y1 - w.y0} nodes per GPU, "
+                               f"{iters} SOR iterations, velocity + dye advection"
+                               + (", 4x RGB565 frame every step" if frame is not None else ""),
                    "grid": [gx, gy], "process_grid": [px, py], "ghost": dec.ghost, "sor_t": sor_t, "halo": mode, "static_advect_halo": static_halo,
                    "halo_exchanges_per_step": (sim.exchanges - ex0) / args.steps,
                    "l2": "per-GPU state exceeds the 126 MB L2; no flush needed",

@@ -168,6 +168,18 @@ class Context:
         check(self._L.fs_sor_half_sweep(a_p, a_d, dim_x, dim_y, dx, omega, parity, self._h),
               "fs_sor_half_sweep")
 
+    def poisson_residual(self, p, div, dim_x, dim_y, dx) -> tuple[float, float]:
+        """(max |r|, ||r||_2) of r = gs(p) - p; device tensors."""
+        n = dim_x * dim_y
+        a_p, d0 = _ptr(p, "float32", n)
+        a_d, d1 = _ptr(div, "float32", n)
+        if not (d0 and d1):
+            raise ValueError("poisson_residual: device tensors only")
+        m, l2 = C.c_float(), C.c_double()
+        check(self._L.fs_poisson_residual(C.byref(m), C.byref(l2), a_p, a_d, dim_x, dim_y, dx, self._h),
+              "fs_poisson_residual")
+        return m.value, l2.value
+
     def apply_drags(self, v, drags, dim_x, dim_y):
         a_v, d0 = _ptr(v, "float32", 2 * dim_x * dim_y)
         if not d0:

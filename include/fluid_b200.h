@@ -67,7 +67,9 @@ int  fs_ctx_synchronize(fs_ctx *ctx);
  *              next tile is prefetched by TMA (3 is the default; falls back to 1 when rows are
  *              not 16-byte multiples)
  *   "advect" : 0 = direct L1/L2 gather, 1 = TMA-staged shared-memory tile (default where legal)
- *   "fuse"   : 0 = fs_step runs the operators one by one, 1 = divergence/gradient fused into SOR passes */
+ *   "fuse"   : bit mask for fs_step: 1 = drags + divergence folded into the velocity advect, 2 =
+ *              gradient-subtract folded into the dye advect (measured slower than the stand-alone
+ *              gradient kernel, which runs at the HBM roofline); 0 = one kernel per operator; default 1 */
 int  fs_ctx_set_option(fs_ctx *ctx, const char *name, int value);
 int  fs_ctx_get_option(fs_ctx *ctx, const char *name, int *value);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
@@ -98,6 +100,12 @@ int fs_poisson_solve(float *p, const float *div, int dim_x, int dim_y, float dx,
 /* one colour of domain_iter_red_black, poisson.cpp:14-61 (parity 0 = (i+j) even = the reference's first pass). */
 int fs_sor_half_sweep(float *p, const float *div, int dim_x, int dim_y, float dx,
                       float omega, int parity, fs_ctx *ctx);
+/* Residual of the system poisson_solve relaxes (not in the reference; a convergence probe):
+ * r_ij = gs_ij(p) - p_ij with gs the Gauss-Seidel value of poisson.cpp:63-90,101-109.
+ * *max_abs = max |r| (exact), *l2 = sqrt(sum r^2) accumulated in double; reduced on the device
+ * with warp shuffles.  Results land in HOST memory; synchronises the stream. */
+int fs_poisson_residual(float *max_abs, double *l2, const float *p, const float *div, int dim_x,
+                        int dim_y, float dx, fs_ctx *ctx);
 /* drag overwrite, ino:264-269.  `drags` is a HOST array (it is the touch queue);
  * records outside the grid are dropped (the reference writes out of bounds). */
 int fs_apply_drags(fs_vec2f *v, const fs_drag *drags, int n, int dim_x, int dim_y,

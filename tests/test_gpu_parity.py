@@ -165,7 +165,7 @@ def run_steps(ctx, v, c, drags_per_step, iters, want_fields=True):
     return to_host(dv), to_host(dc, np.uint32), to_host(dp), to_host(dd)
 
 
-@pytest.mark.parametrize("fuse", [0, 1], ids=["unfused", "fused"])
+@pytest.mark.parametrize("fuse", [0, 1, 2, 3], ids=["unfused", "fuse-div", "fuse-grad", "fused"])
 @pytest.mark.parametrize("shape,iters,steps", [((61, 81), 10, 100), ((80, 60), 10, 20), ((7, 3), 10, 5),
                                                ((2, 2), 3, 3), ((300, 260), 50, 3), ((1024, 1024), 50, 2)])
 def test_step_matches_oracle(ctx, oracle, shape, iters, steps, fuse):
@@ -325,3 +325,23 @@ def test_ensemble_too_large_is_unsupported(ctx):
     with pytest.raises(fb.FluidError) as e:
         ctx.ensemble_step(v, c, 1, 128, 128, DT, 1.0, 10, 1.96)
     assert e.value.code == FS_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("shape", [(5, 4), (61, 81), (512, 300)])
+def test_poisson_residual(ctx, oracle, shape):
+    """Residual probe (warp-shuffle reduction): max |gs(p) - p| is exact, the 2-norm to 1e-6."""
+    dim_x, dim_y = shape
+    rng = np.random.default_rng(21)
+    d = rng.normal(0, 5, (dim_y, dim_x)).astype(np.float32)
+    for iters in (0, 5, 40):
+        p = oracle.poisson_solve(d, 1.0, iters, 1.96)
+        q = p.copy()                                           # one Gauss-Seidel value per node from the SAME p:
+        ge = oracle.sor_half_sweep(p.copy(), d, 1.0, 1.0, 0)   # omega = 1 turns the SOR update into gs itself
+        go = oracle.sor_half_sweep(p.copy(), d, 1.0, 1.0, 1)
+        jj, ii = np.indices(p.shape)
+        gs = np.where((ii + jj) % 2 == 0, ge, go)
+        r = (gs - q).astype(np.float32)
+        m, l2 = ctx.poisson_residual(to_dev(p), to_dev(d), dim_x, dim_y, 1.0)
+        assert np.float32(m) == np.abs(r).max()
+        assert abs(l2 - np.sqrt((r.astype(np.float64) ** 2).sum())) <= 1e-6 * max(l2, 1e-30)
+        assert np.isfinite(l2)
