@@ -20,9 +20,9 @@
 
 namespace fs {
 
-constexpr int ENS_THREADS = 1024;
-constexpr int ENS_MAX_ROUNDS = 3;                                   // pairs per thread
-constexpr int ENS_MAX_NODES = 2 * ENS_THREADS * ENS_MAX_ROUNDS;     // also bounded by smem (40 B/node)
+constexpr int ENS_MAX_THREADS = 1024;
+constexpr int ENS_MAX_ROUNDS = 3;                                       // pairs per thread
+constexpr int ENS_MAX_NODES = 2 * ENS_MAX_THREADS * ENS_MAX_ROUNDS;     // also bounded by smem (40 B/node)
 
 template <class P>
 struct SmemFetch {
@@ -46,8 +46,11 @@ struct EnsArgs {
     SorCoef k;
 };
 
-__global__ void __launch_bounds__(ENS_THREADS, 1) ensemble_kernel(const EnsArgs a)
+__global__ void __launch_bounds__(ENS_MAX_THREADS, 1) ensemble_kernel(const EnsArgs a)
 {
+    // the CTA is sized by the launcher so that the node pairs divide (almost) evenly over the threads:
+    // every phase ends in a barrier, and idle threads in the last round were the top stall (ncu)
+    const int ENS_THREADS = blockDim.x;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.dim_x * a.dim_y, dim_x = a.dim_x, dim_y = a.dim_y;
     float2 *A = reinterpret_cast<float2 *>(smem_raw);
@@ -247,7 +250,12 @@ int launch_ensemble(const Launch &L, float2 *v, uint32_t *c, const fs_drag *drag
     cudaError_t e = cudaFuncSetAttribute(ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int grid = batch < L.num_sms ? batch : L.num_sms;   // persistent: one CTA per SM walks the batch
-    ensemble_kernel<<<grid, ENS_THREADS, smem, L.stream>>>(a);
+    // threads: ENS_MAX_ROUNDS pairs per thread, rounded up to whole warps (80x60 -> 800, 61x81 -> 832)
+    const int pairs = (dim_x * dim_y + 1) / 2;
+    int threads = ((pairs + ENS_MAX_ROUNDS - 1) / ENS_MAX_ROUNDS + 31) / 32 * 32;
+    if (threads < 128) threads = 128;
+    if (threads > ENS_MAX_THREADS) threads = ENS_MAX_THREADS;
+    ensemble_kernel<<<grid, threads, smem, L.stream>>>(a);
     ++*L.launches;
     return (int)cudaGetLastError();
 }
