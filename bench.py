@@ -174,6 +174,7 @@ def run_b200_arm(args):
 
     if world > 1:
         from esp32_fluid_simulation_b200 import dist as fdist
+        args.clock_sampler = ClockSampler
         result = fdist.bench_decomposed(args, GRID, args.iters, N_DRAGS)
     else:
         result = bench_single(args, fb, synth, torch)

@@ -489,22 +489,63 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
     torch.cuda.synchronize()
     launches0, ex0 = ops.ctx.launch_count, sim.exchanges
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = getattr(args, "clock_sampler", None)
+    clk = sampler(local_rank).__enter__() if (sampler and rank == 0) else None
     t0 = time.perf_counter()
     e0.record()
     for s in range(args.warmup, args.warmup + args.steps):
         one_step(s)
     e1.record()
     torch.cuda.synchronize()
+    launches, exchanges = ops.ctx.launch_count - launches0, sim.exchanges - ex0
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    if clk is not None:
+        t_busy = time.time() + 0.3          # keep the device busy so the 100 ms sampler sees loaded clocks
+        while time.time() < t_busy:
+            ops.ctx.tile_calculate_divergence(sim.div, sim.v, ops._tile(w), synth.DX)
+        torch.cuda.synchronize()
+        clk.__exit__(None, None, None)
+    clocks = clk.summary() if clk is not None else None
     if static_halo is not None:
         sim.check()              # no advect of the timed region read outside its window
     dist.barrier()
     torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3
     t = torch.tensor([e0.elapsed_time(e1), wall_ms], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0].item()) / args.steps
     nodes = gx * gy
     value = nodes / (ms * 1e-3) / 1e6
+
+    # ---- e2e: every rank's state starts and ends in pinned HOST memory, every step ----
+    hv = torch.from_numpy(synth.velocity(gx, gy, window=(w.ox, w.oy, w.nx, w.ny))).pin_memory()
+    hc = torch.from_numpy(synth.dye(gx, gy, window=(w.ox, w.oy, w.nx, w.ny)).view(np.int32)).pin_memory()
+    ov = torch.empty((w.y1 - w.y0, w.x1 - w.x0, 2), dtype=torch.float32).pin_memory()
+    oc = torch.empty((w.y1 - w.y0, w.x1 - w.x0, 3), dtype=torch.int32).pin_memory()
+    e2e_steps = 3
+
+    def e2e_step(k):
+        sim.v.copy_(hv, non_blocking=True)          # H2D: this rank's window of the state
+        sim.c.copy_(hc, non_blocking=True)
+        sim.v_halo, sim.need_halo = 0, None if static_halo is None else static_halo
+        one_step(k % len(drags))
+        ov.copy_(sim.v[w.y0:w.y1, w.x0:w.x1], non_blocking=True)   # D2H: the rectangle this rank owns
+        oc.copy_(sim.c[w.y0:w.y1, w.x0:w.x1], non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_step(0)
+    dist.barrier()
+    t1 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    dist.barrier()
+    te = torch.tensor([(time.perf_counter() - t1) / e2e_steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    own_nodes = (w.x1 - w.x0) * (w.y1 - w.y0)
+    e2e = {"value": nodes / e2e_s / 1e6, "unit": "Mcell-steps/s", "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "h2d_bytes_per_step": int(w.nx * w.ny * 20 + 12 * n_drags) * world,
+           "d2h_bytes_per_step": int(own_nodes * 20) * world,
+           "api": "DecomposedSim: pinned host window -> device, step, owned rectangle -> pinned host (every rank)"}
     return {
         "metric": "Mcell-steps/s (advect+project, 50 SOR iters) at 4096^2", "value": value,
         "unit": "Mcell-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -514,10 +555,10 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
                                f"{iters} SOR iterations, velocity + dye advection"
                                + (", 4x RGB565 frame every step" if frame is not None else ""),
                    "grid": [gx, gy], "process_grid": [px, py], "ghost": dec.ghost, "sor_t": sor_t, "halo": mode, "static_advect_halo": static_halo,
-                   "halo_exchanges_per_step": (sim.exchanges - ex0) / args.steps,
+                   "halo_exchanges_per_step": exchanges / args.steps,
                    "l2": "per-GPU state exceeds the 126 MB L2; no flush needed",
                    "timing": "CUDA events on the compute stream, max over ranks"},
         "wall_ms_per_step_max": float(t[1].item()) / args.steps,
-        "gpu_launches": int(ops.ctx.launch_count - launches0),
-        "e2e": None, "roofline": None, "cpu_baseline": None,
+        "gpu_launches": int(launches),
+        "clocks": clocks, "e2e": e2e, "roofline": None, "cpu_baseline": None,
     }
