@@ -93,6 +93,13 @@ def main():
         ctx.set_option("sor", 0)
         run_sor("[half-sweeps]")
         ctx.set_option("sor", 1)
+        for shape in (2, 3, 5):
+            for t in (4, 6, 8):
+                ctx.set_option("sor_shape", shape)
+                ctx.set_option("sor_t", t)
+                ctx.set_option("sor_one_launch", 1)
+                run_sor(f"[one-launch shape={shape} T={t}]")
+        ctx.set_option("sor_one_launch", 0)
         for shape in (0, 2, 3, 4, 5, 6):
             ctx.set_option("sor_shape", shape)
             for t in (2, 4, 6, 8):
@@ -100,6 +107,7 @@ def main():
                 run_sor(f"[blocked shape={shape} T={t}]")
         ctx.set_option("sor_shape", 3)
         ctx.set_option("sor_t", 8)
+        ctx.set_option("sor_one_launch", 0)
         for fuse in (0, 1, 2, 3):
             ctx.set_option("fuse", fuse)
             run_step(f"[fuse={fuse}]")

@@ -11,7 +11,7 @@
 using namespace fs;
 
 constexpr int WORK_SLOTS = 64;
-enum Scratch { S_VTMP = 0, S_CTMP, S_DIV, S_P, S_P2, S_HV, S_HV2, S_HC, S_HC2, S_HP, S_HD, S_HIMG, S_EDRAG, S_ECNT, S_COUNT };
+enum Scratch { S_VTMP = 0, S_CTMP, S_DIV, S_P, S_P2, S_HV, S_HV2, S_HC, S_HC2, S_HP, S_HD, S_HIMG, S_EDRAG, S_ECNT, S_SOLVE_FLAGS, S_COUNT };
 
 struct fs_ctx {
     int device;
@@ -28,6 +28,8 @@ struct fs_ctx {
     cudaStream_t copy_in, copy_out;   // side streams of fsh_step: PCIe copies overlap the compute
     cudaEvent_t ev_start, ev_c_in, ev_v_done;
     size_t max_smem_optin;
+    unsigned int solve_gen;     // generation stamp of the single-launch solve's completion flags
+    int opt_sor_one_launch;
     int opt_sor, opt_sor_t, opt_sor_shape, opt_advect, opt_fuse;
 };
 
@@ -142,6 +144,24 @@ int core_poisson_solve(fs_ctx *ctx, float *p, const float *div, const Geo &g, fl
         void *scratch;
         int e = ensure(ctx, S_P2, sizeof(float) * (size_t)g.nx * g.ny, &scratch);
         if (e) return e;
+        if (ctx->opt_sor_one_launch == 1) {
+            // all passes in ONE persistent launch (tile-level dependencies instead of kernel boundaries)
+            const size_t need = sor_solve_flag_count(g, iters, T);
+            void *flags;
+            const bool fresh = ctx->scratch_bytes[S_SOLVE_FLAGS] < need * sizeof(unsigned int);
+            if ((e = ensure(ctx, S_SOLVE_FLAGS, need * sizeof(unsigned int), &flags))) return e;
+            if (fresh)
+                FS_CUDA_TRY(cudaMemsetAsync(flags, 0, ctx->scratch_bytes[S_SOLVE_FLAGS], ctx->stream));
+            if (++ctx->solve_gen == 0) {   // stamp wrapped: start over from clean flags
+                FS_CUDA_TRY(cudaMemsetAsync(flags, 0, ctx->scratch_bytes[S_SOLVE_FLAGS], ctx->stream));
+                ctx->solve_gen = 1;
+            }
+            FS_CUDA_TRY(cudaMemsetAsync(ctx->work_dev, 0, sizeof(int), ctx->stream));
+            e = launch_sor_solve(mk(ctx), p, (float *)scratch, div, g, dx, omega, iters, T, ctx->opt_sor_shape,
+                                 ctx->work_dev, (unsigned int *)flags,
+                                 ctx->scratch_bytes[S_SOLVE_FLAGS] / sizeof(unsigned int), ctx->solve_gen);
+            if (e >= 0) return e;          // launched (or a CUDA error); -1 = not eligible, fall through
+        }
         float *bufs[2] = {(passes & 1) ? p : (float *)scratch, (passes & 1) ? (float *)scratch : p};
         const float *src = nullptr;
         int done = 0;
@@ -260,6 +280,7 @@ int fs_ctx_create(fs_ctx **out, int device, void *stream)
     ctx->opt_sor = 1;
     ctx->opt_sor_t = 8;
     ctx->opt_sor_shape = 3;
+    ctx->opt_sor_one_launch = 0;
     ctx->opt_advect = 1;
     ctx->opt_fuse = 1;
     cudaError_t e = cudaMalloc(&ctx->status_dev, sizeof(int));
@@ -311,6 +332,7 @@ static int *opt_slot(fs_ctx *ctx, const char *name)
     if (!strcmp(name, "sor")) return &ctx->opt_sor;
     if (!strcmp(name, "sor_t")) return &ctx->opt_sor_t;
     if (!strcmp(name, "sor_shape")) return &ctx->opt_sor_shape;
+    if (!strcmp(name, "sor_one_launch")) return &ctx->opt_sor_one_launch;
     if (!strcmp(name, "advect")) return &ctx->opt_advect;
     if (!strcmp(name, "fuse")) return &ctx->opt_fuse;
     return nullptr;

@@ -64,6 +64,13 @@ int launch_ensemble(const Launch &L, float2 *v, uint32_t *c, const fs_drag *drag
                     const int *counts_dev, int max_drags, int batch, int dim_x, int dim_y, float dt,
                     float dx, int iters, float omega, int n_steps);
 
+// the whole solve in ONE persistent launch with tile-level dependencies between passes; returns -1
+// when not eligible (caller falls back to one launch per pass)
+size_t sor_solve_flag_count(const Geo &g, int iters, int t_block);
+int launch_sor_solve(const Launch &L, float *p, float *scratch, const float *div, const Geo &g, float dx,
+                     float omega, int iters, int t_block, int shape, int *work_counter, unsigned int *done,
+                     size_t done_capacity, unsigned int gen);
+
 // halo.cu — one-kernel halo exchange over peer (NVLink) memory
 constexpr int HALO_MAX_COPIES = 32, HALO_MAX_PEERS = 8;
 struct HaloCopy {

@@ -121,13 +121,13 @@ __device__ __forceinline__ void strip_half_sweep(float (&p)[R][4], const float (
 // all H half-sweeps of one pass over a warp's strip, with the inter-warp row mailbox
 template <int R, int NW, bool WALL>
 __device__ __forceinline__ void sweep_pass(float (&p)[R][4], const float (&dxd)[R][4], const BlockedArgs &a,
-                                           float4 (*mail)[NW][2][32], int gi0, int gj0)
+                                           float4 (*mail)[NW][2][32], int gi0, int gj0, int n_half)
 {
     const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
     // colour bookkeeping: node (column c, row r) of this strip has global parity (c + r + pb) & 1
     const int pb = (gi0 + gj0) & 1;
     float dn[4] = {0.f, 0.f, 0.f, 0.f}, up[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < a.n_half; s++) {
+    for (int s = 0; s < n_half; s++) {
         const int buf = s & 1;
         mail[buf][w][0][t] = make_float4(p[0][0], p[0][1], p[0][2], p[0][3]);
         mail[buf][w][1][t] = make_float4(p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3]);
@@ -148,8 +148,8 @@ __device__ __forceinline__ void sweep_pass(float (&p)[R][4], const float (&dxd)[
 
 // write back the tile interior, clipped to the compute rectangle
 template <int R>
-__device__ __forceinline__ void store_tile(const float (&p)[R][4], const BlockedArgs &a, int rlx0, int rly0,
-                                           int lx0, int ly0)
+__device__ __forceinline__ void store_tile(const float (&p)[R][4], const BlockedArgs &a, float *p_out, int rlx0,
+                                           int rly0, int lx0, int ly0)
 {
     const Geo &g = a.g;
     const int ox0 = max(rlx0 + a.hpx, g.x0), ox1 = min(rlx0 + a.hpx + a.tw_out, g.x1);
@@ -159,7 +159,7 @@ __device__ __forceinline__ void store_tile(const float (&p)[R][4], const Blocked
     for (int r = 0; r < R; r++) {
         const int ly = ly0 + r;
         if (ly < oy0 || ly >= oy1) continue;
-        float *row = a.p_out + (size_t)ly * g.nx;
+        float *row = p_out + (size_t)ly * g.nx;
         if (cols_full && a.vec_ok) {
             *reinterpret_cast<float4 *>(row + lx0) = make_float4(p[r][0], p[r][1], p[r][2], p[r][3]);
         } else {
@@ -180,6 +180,12 @@ __device__ __forceinline__ void tile_coords(int idx, int ntx, int nty, int &tx, 
     else if (idx < 2 * ntx) { tx = idx - ntx; ty = nty - 1; }
     else if (idx < frame) { const int k = idx - 2 * ntx; tx = (k & 1) ? ntx - 1 : 0; ty = 1 + (k >> 1); }
     else { const int k = idx - frame; tx = 1 + k % (ntx - 2); ty = 1 + k / (ntx - 2); }
+}
+
+__device__ __forceinline__ void rowmajor_coords(int idx, int ntx, int &tx, int &ty)
+{
+    ty = idx / ntx;
+    tx = idx - ty * ntx;
 }
 
 // does a region touch a domain wall or stick out of the domain?  (CTA-uniform)
@@ -231,9 +237,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) sor_blocked_kernel(const Blocke
             }
         }
     }
-    if (!region_hits_wall<R, NW>(a, rlx0, rly0)) sweep_pass<R, NW, false>(p, dxd, a, mail, gi0, gj0);
-    else                                          sweep_pass<R, NW, true>(p, dxd, a, mail, gi0, gj0);
-    store_tile<R>(p, a, rlx0, rly0, lx0, ly0);
+    if (!region_hits_wall<R, NW>(a, rlx0, rly0)) sweep_pass<R, NW, false>(p, dxd, a, mail, gi0, gj0, a.n_half);
+    else                                          sweep_pass<R, NW, true>(p, dxd, a, mail, gi0, gj0, a.n_half);
+    store_tile<R>(p, a, a.p_out, rlx0, rly0, lx0, ly0);
 }
 
 // ---- loader 2: persistent CTAs, next tile prefetched into shared memory by TMA -----------------
@@ -308,9 +314,155 @@ sor_blocked_tma_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_c
         }
         __syncthreads();                       // every warp has drained the staging buffers
         if (threadIdx.x == 0) claim_and_prefetch((it + 1) & 1);   // visible after sweep_pass's first barrier
-        if (!region_hits_wall<R, NW>(a, rlx0, rly0)) sweep_pass<R, NW, false>(p, dxd, a, mail, gi0, gj0);
-        else                                          sweep_pass<R, NW, true>(p, dxd, a, mail, gi0, gj0);
-        store_tile<R>(p, a, rlx0, rly0, lx0, ly0);
+        if (!region_hits_wall<R, NW>(a, rlx0, rly0)) sweep_pass<R, NW, false>(p, dxd, a, mail, gi0, gj0, a.n_half);
+        else                                          sweep_pass<R, NW, true>(p, dxd, a, mail, gi0, gj0, a.n_half);
+        store_tile<R>(p, a, a.p_out, rlx0, rly0, lx0, ly0);
+    }
+}
+
+// ---- loader 3: the WHOLE solve in one persistent launch ------------------------------------------
+// Work item w = (pass k, tile): claimed in order from one atomic counter; tiles in ROW-MAJOR order
+// inside a pass, so the items a tile depends on (rows <= ty+1 of the previous pass) were claimed
+// about a whole pass earlier and are long complete — only the very first launch-wide wave can wait.
+// (Wall-tiles-first, the order of the per-pass kernel, made the bottom frame row of pass k wait for
+// the LAST interior row of pass k-1 and idled dozens of SMs at every pass boundary: 1.08 ms.)  A tile of pass k >= 1
+// reads p over its region from the buffer pass k-1 wrote, so it depends on the 3x3 neighbourhood of
+// tiles of pass k-1 (region = tile + halo <= one tile on every side); the same wait also covers the
+// write-after-read hazard of the ping-pong (pass k writes the buffer pass k-1 read: its readers of
+// this tile's area are exactly those 3x3 neighbours).  Completion is published per tile with a
+// release store of the solve's generation number and observed with acquire loads by the thread
+// that issues the TMA prefetch.  The prefetch of the NEXT item is issued early if its dependencies
+// are already met, otherwise after this CTA has published its own tile (never blocking before its
+// own work is done: every dependency has a smaller work index, so waits cannot form a cycle).
+// No global barrier between passes: launch gaps, pipeline ramps and per-pass tails disappear.
+// MEASURED (4096^2, K=50): 0.98-1.11 ms against 0.87-0.88 ms for one launch per pass — the nine
+// ld.acquire.gpu probes (~3 us, serialised by their acquire semantics) and the release fence run on
+// thread 0, which is also a compute lane, so every warp waits for them at the tile's first barrier;
+// that costs more than the gaps and tails it removes.  Kept as an option ("sor_one_launch"), not
+// the default; a dedicated producer warp would be the next thing to try.
+//   profiles/r01_kernel_sweep_sor_one_launch.json
+struct SolveArgs {
+    BlockedArgs a;            // geometry + coefficients; n_half = half-sweeps of a regular pass
+    float *buf[2];            // buf[k & 1] is written by pass k
+    int passes, n_half_last;
+    int ntx, nty;
+    int *work_counter;        // zeroed before the launch
+    unsigned int *done;       // [passes][ntx*nty] generation stamps
+    unsigned int gen;
+};
+
+template <int R, int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB)
+sor_solve_tma_kernel(const __grid_constant__ CUtensorMap d_map, const __grid_constant__ CUtensorMap p0_map,
+                     const __grid_constant__ CUtensorMap p1_map, const SolveArgs sa)
+{
+    constexpr int RH = R * NW;
+    const BlockedArgs &a = sa.a;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4 *sd = reinterpret_cast<float4 *>(smem);
+    float4 *sp = sd + RH * 32;
+    float4 (*mail)[NW][2][32] = reinterpret_cast<float4 (*)[NW][2][32]>(sp + RH * 32);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int s_item[2];
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+    const Geo &g = a.g;
+    const int n_tiles = sa.ntx * sa.nty, total = sa.passes * n_tiles;
+    const uint32_t region_bytes = RH * BLK_RW * 4u;
+
+    auto deps_ready = [&](int item) -> bool {
+        const int k = item / n_tiles;
+        if (k == 0) return true;
+        int tx, ty;
+        rowmajor_coords(item - k * n_tiles, sa.ntx, tx, ty);
+        const unsigned int *flags = sa.done + (size_t)(k - 1) * n_tiles;
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                const int x = tx + dx, y = ty + dy;
+                if (x < 0 || x >= sa.ntx || y < 0 || y >= sa.nty) continue;
+                unsigned int seen;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags + y * sa.ntx + x) : "memory");
+                if (seen != sa.gen) return false;
+            }
+        return true;
+    };
+    auto issue = [&](int item) {
+        const int k = item / n_tiles;
+        int tx, ty;
+        rowmajor_coords(item - k * n_tiles, sa.ntx, tx, ty);
+        const int x = a.lax + tx * a.tw_out - a.hpx, y = a.lay + ty * a.th_out - a.hpy;
+        asm volatile("fence.proxy.async;" ::: "memory");   // other CTAs' generic stores -> this CTA's async-proxy reads
+        mbar_expect_tx(&bar, k > 0 ? 2u * region_bytes : region_bytes);
+        tma_load_2d(sd, &d_map, x, y, &bar);
+        if (k > 0) tma_load_2d(sp, ((k - 1) & 1) ? &p1_map : &p0_map, x, y, &bar);
+    };
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const int first = atomicAdd(sa.work_counter, 1);
+        s_item[0] = first;
+        if (first < total) {
+            while (!deps_ready(first)) __nanosleep(100);
+            issue(first);
+        }
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    for (int it = 0;; it++) {
+        const int item = s_item[it & 1];
+        if (item >= total) break;
+        const int k = item / n_tiles, idx = item - k * n_tiles;
+        int tx, ty;
+        rowmajor_coords(idx, sa.ntx, tx, ty);
+        const int rlx0 = a.lax + tx * a.tw_out - a.hpx;
+        const int rly0 = a.lay + ty * a.th_out - a.hpy;
+        const int lx0 = rlx0 + 4 * t, ly0 = rly0 + w * R;
+        const int gi0 = g.ox + lx0, gj0 = g.oy + ly0;
+
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        float p[R][4], dxd[R][4];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float4 dv = sd[(w * R + r) * 32 + t];
+            dxd[r][0] = __fmul_rn(a.k.dx, dv.x);
+            dxd[r][1] = __fmul_rn(a.k.dx, dv.y);
+            dxd[r][2] = __fmul_rn(a.k.dx, dv.z);
+            dxd[r][3] = __fmul_rn(a.k.dx, dv.w);
+            if (k > 0) {
+                const float4 pv = sp[(w * R + r) * 32 + t];
+                p[r][0] = pv.x; p[r][1] = pv.y; p[r][2] = pv.z; p[r][3] = pv.w;
+            } else {
+                p[r][0] = p[r][1] = p[r][2] = p[r][3] = 0.0f;
+            }
+        }
+        __syncthreads();                       // every warp has drained the staging buffers
+        int next = total;
+        bool issued = true;
+        if (threadIdx.x == 0) {
+            next = atomicAdd(sa.work_counter, 1);
+            s_item[(it + 1) & 1] = next;       // visible after sweep_pass's first barrier
+            issued = next >= total;
+            if (!issued && deps_ready(next)) {
+                issue(next);
+                issued = true;
+            }
+        }
+        const int n_half = k == sa.passes - 1 ? sa.n_half_last : a.n_half;
+        if (!region_hits_wall<R, NW>(a, rlx0, rly0)) sweep_pass<R, NW, false>(p, dxd, a, mail, gi0, gj0, n_half);
+        else                                          sweep_pass<R, NW, true>(p, dxd, a, mail, gi0, gj0, n_half);
+        store_tile<R>(p, a, sa.buf[k & 1], rlx0, rly0, lx0, ly0);
+        __syncthreads();                       // the whole tile has been stored
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sa.done + (size_t)k * n_tiles + ty * sa.ntx + tx),
+                         "r"(sa.gen)
+                         : "memory");
+            if (!issued) {                     // the next item waits on tiles still in flight (pass boundary)
+                while (!deps_ready(next)) __nanosleep(100);
+                issue(next);
+            }
+        }
     }
 }
 
@@ -362,6 +514,81 @@ static int launch_cfg_tma(const Launch &L, BlockedArgs &a, int *work_counter)
     sor_blocked_tma_kernel<R, NW, MINB><<<grid, 32 * NW, smem, L.stream>>>(p_map, d_map, a, ntx, nty, work_counter);
     ++*L.launches;
     return (int)cudaGetLastError();
+}
+
+template <int R, int NW, int MINB>
+static int launch_solve_cfg(const Launch &L, SolveArgs &sa)
+{
+    BlockedArgs &a = sa.a;
+    const Geo &g = a.g;
+    int ntx, nty;
+    if (!tile_cfg<R, NW>(a, ntx, nty)) return -1;
+    if (ntx <= 0 || nty <= 0 || a.hpx > a.tw_out || a.hpy > a.th_out) return -1;   // halo must stay inside the 3x3
+    if ((long long)ntx * nty * sa.passes > 0x3fffffff) return -1;
+    sa.ntx = ntx;
+    sa.nty = nty;
+    CUtensorMap d_map, p0_map, p1_map;
+    if (!tma_make_map_2d(&d_map, a.div, g.nx, g.ny, g.nx, BLK_RW, R * NW) ||
+        !tma_make_map_2d(&p0_map, sa.buf[0], g.nx, g.ny, g.nx, BLK_RW, R * NW) ||
+        !tma_make_map_2d(&p1_map, sa.buf[1], g.nx, g.ny, g.nx, BLK_RW, R * NW))
+        return (int)cudaErrorInvalidValue;
+    const size_t smem = (size_t)2 * R * NW * BLK_RW * 4 + sizeof(float4) * 2 * NW * 2 * 32;
+    cudaError_t e = cudaFuncSetAttribute(sor_solve_tma_kernel<R, NW, MINB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const long long total = (long long)ntx * nty * sa.passes;
+    const int grid = total < MINB * L.num_sms ? (int)total : MINB * L.num_sms;
+    sor_solve_tma_kernel<R, NW, MINB><<<grid, 32 * NW, smem, L.stream>>>(d_map, p0_map, p1_map, sa);
+    ++*L.launches;
+    return (int)cudaGetLastError();
+}
+
+// Flags needed by launch_sor_solve for a grid: passes * tiles (upper bound over the shapes).
+size_t sor_solve_flag_count(const Geo &g, int iters, int t_block)
+{
+    const int passes = (iters + t_block - 1) / t_block;
+    const long long tiles = (long long)((g.x1 - g.x0) / 64 + 3) * ((g.y1 - g.y0) / 32 + 3);   // generous
+    return (size_t)(passes * tiles);
+}
+
+// The whole solve (iters full iterations, t_block per pass) in ONE launch.  p is the caller's
+// buffer (receives the result), scratch the ping-pong partner.  Returns -1 when the configuration
+// is not eligible (the caller then uses one launch per pass).
+int launch_sor_solve(const Launch &L, float *p, float *scratch, const float *div, const Geo &g, float dx,
+                     float omega, int iters, int t_block, int shape, int *work_counter, unsigned int *done,
+                     size_t done_capacity, unsigned int gen)
+{
+    if (iters <= 0 || t_block <= 0 || g.x1 <= g.x0 || g.y1 <= g.y0) return -1;
+    if (2 * t_block > SOR_BLOCKED_MAX_HALF) return -1;
+    const bool vec_ok = (g.nx % 4 == 0) && ((uintptr_t)p % 16 == 0) && ((uintptr_t)scratch % 16 == 0) &&
+                        ((uintptr_t)div % 16 == 0);
+    if (!vec_ok || !work_counter || !done || tma_encode_fn() == nullptr) return -1;
+    SolveArgs sa;
+    BlockedArgs &a = sa.a;
+    a.p_out = nullptr;
+    a.p_in = nullptr;
+    a.div = div;
+    a.g = g;
+    a.k = make_sor_coef(dx, omega);
+    a.first_parity = 0;
+    a.vec_ok = 1;
+    sa.passes = (iters + t_block - 1) / t_block;
+    const int t_last = iters - (sa.passes - 1) * t_block;
+    a.n_half = sa.passes > 1 ? 2 * t_block : 2 * t_last;   // tile geometry follows the regular pass
+    sa.n_half_last = 2 * t_last;
+    // the LAST pass must land in the caller's buffer
+    sa.buf[(sa.passes - 1) & 1] = p;
+    sa.buf[sa.passes & 1] = scratch;
+    sa.work_counter = work_counter;
+    sa.done = done;
+    sa.gen = gen;
+    if (sor_solve_flag_count(g, iters, t_block) > done_capacity) return -1;
+    switch (shape) {
+        case 2: return launch_solve_cfg<12, 8, 2>(L, sa);
+        case 3: return launch_solve_cfg<12, 16, 1>(L, sa);
+        case 5: return launch_solve_cfg<10, 16, 1>(L, sa);
+        default: return -1;
+    }
 }
 
 int launch_sor_blocked(const Launch &L, float *p_out, const float *p_in, const float *div, const Geo &g,

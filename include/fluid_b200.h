@@ -66,6 +66,10 @@ int  fs_ctx_synchronize(fs_ctx *ctx);
  *              loaded straight from global; 2 / 3 = the same regions with persistent CTAs whose
  *              next tile is prefetched by TMA (3 is the default; falls back to 1 when rows are
  *              not 16-byte multiples)
+ *   "sor_one_launch": 1 = all passes of a solve run in ONE persistent launch with tile-level
+ *              dependencies between passes (shapes 2, 3, 5); 0 (default) = one launch per pass.
+ *              Measured: the dependency probes and release fences on the issuing thread cost more
+ *              than the launch gaps and per-pass tails they remove (0.98 vs 0.87 ms at 4096^2)
  *   "advect" : 0 = direct L1/L2 gather, 1 = TMA-staged shared-memory tile (default where legal)
  *   "fuse"   : bit mask for fs_step: 1 = drags + divergence folded into the velocity advect, 2 =
  *              gradient-subtract folded into the dye advect (measured slower than the stand-alone

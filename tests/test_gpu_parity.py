@@ -97,11 +97,15 @@ def test_poisson_solve(ctx, oracle, sor_variant, shape, iters, omega, dx):
 
 @pytest.mark.parametrize("shape", [0, 1, 2, 3, 4, 5, 6],
                          ids=["direct-96", "direct-192", "tma-96", "tma-192", "tma-144", "tma-160", "tma-192b"])
+@pytest.mark.parametrize("one_launch", [1, 0], ids=["one-launch", "launch-per-pass"])
 @pytest.mark.parametrize("t_block", [1, 2, 3, 4, 6, 8])
-def test_poisson_solve_every_blocking_depth(ctx, oracle, t_block, shape):
+def test_poisson_solve_every_blocking_depth(ctx, oracle, t_block, shape, one_launch):
+    if one_launch and shape not in (2, 3, 5):
+        pytest.skip("single-launch solve exists for shapes 2, 3, 5")
     ctx.set_option("sor", 1)
     ctx.set_option("sor_t", t_block)
     ctx.set_option("sor_shape", shape)
+    ctx.set_option("sor_one_launch", one_launch)
     try:
         for dim_x, dim_y, iters in [(300, 200, 13), (61, 81, 10), (1000, 40, 9), (1024, 1100, 17)]:
             d = np.random.default_rng(7).normal(0, 20, (dim_y, dim_x)).astype(np.float32)
@@ -111,6 +115,7 @@ def test_poisson_solve_every_blocking_depth(ctx, oracle, t_block, shape):
     finally:
         ctx.set_option("sor_t", 8)
         ctx.set_option("sor_shape", 3)
+        ctx.set_option("sor_one_launch", 0)
 
 
 def test_half_sweep_colours(ctx, oracle):
