@@ -385,15 +385,16 @@ class PeerComm:
     torch.distributed is used once, to ship the 64-byte IPC handles."""
 
     def __init__(self, ops: ArenaTileOps, world: int, rank: int, gdim_x: int, gdim_y: int, ghost: int,
-                 grid=None, peer_bases: dict | None = None):
+                 grid=None, peer_bases: dict | None = None, handles: list | None = None):
         self.ops, self.rank, self.world = ops, rank, world
         self.decs = [Decomposition(gdim_x, gdim_y, world, r, ghost, grid) for r in range(world)]
         self.seq = 0
         me = self.decs[rank]
         if peer_bases is None:
-            import torch.distributed as dist
-            handles = [None] * world
-            dist.all_gather_object(handles, ops.ctx.ipc_export(ops.base))
+            if handles is None:
+                import torch.distributed as dist
+                handles = [None] * world
+                dist.all_gather_object(handles, ops.ctx.ipc_export(ops.base))
             peer_bases = {peer: ops.ctx.ipc_open(handles[peer]) for peer, _, _ in me.neighbours()}
             self._opened = list(peer_bases.values())
         self.peer_bases = peer_bases
@@ -440,6 +441,7 @@ def max_window_nodes(gdim_x, gdim_y, world, ghost, grid=None) -> int:
 def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
     """Weak scaling: every GPU owns tile_edge x tile_edge nodes of one global grid."""
     import os
+    import sys
     import time
 
     import torch
@@ -458,9 +460,32 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
     ghost = 64
     mode = os.environ.get("FS_HALO", "peer")        # peer = NVLink stores (default), nccl = send/recv
     dec = Decomposition(gx, gy, world, rank, ghost=ghost)
+    ops = comm = None
     if mode == "peer":
-        ops = ArenaTileOps(local_rank, max_window_nodes(gx, gy, world, ghost))
-        comm = PeerComm(ops, world, rank, gx, gy, ghost)
+        # every rank must end up on the same path: agree on whether the IPC mapping worked everywhere
+        ok, why, handle = 1, "", None
+        try:
+            ops = ArenaTileOps(local_rank, max_window_nodes(gx, gy, world, ghost))
+            handle = ops.ctx.ipc_export(ops.base)
+        except Exception as e:  # noqa: BLE001 — e.g. CUDA IPC not permitted in this container
+            ok, why = 0, f"{type(e).__name__}: {e}"
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)     # every rank takes part, whatever happened above
+        if ok and all(h is not None for h in handles):
+            try:
+                comm = PeerComm(ops, world, rank, gx, gy, ghost, handles=handles)
+            except Exception as e:  # noqa: BLE001
+                ok, why = 0, f"{type(e).__name__}: {e}"
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if rank == 0:
+                print(f"[bench] peer-memory halos unavailable ({why or 'another rank failed'}); using NCCL send/recv",
+                      file=sys.stderr, flush=True)
+            mode, ops, comm = "nccl", None, None
+    if mode == "peer":
         static_halo = 48     # covers the 34-node backtraces of the +-1000 nodes/s synthetic drags
     else:
         ops = CudaTileOps(local_rank)
