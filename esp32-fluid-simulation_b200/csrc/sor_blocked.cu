@@ -281,8 +281,11 @@ sor_blocked_tma_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_c
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        claim_and_prefetch(0);
     }
+    // Programmatic dependent launch: this grid may have been scheduled while the previous pass was
+    // still draining; everything above overlapped with it, nothing below may (p_in is its output).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0) claim_and_prefetch(0);
     __syncthreads();
     uint32_t phase = 0;
     for (int it = 0;; it++) {
@@ -511,9 +514,19 @@ static int launch_cfg_tma(const Launch &L, BlockedArgs &a, int *work_counter)
     if (e != cudaSuccess) return (int)e;
     const int n_tiles = ntx * nty;
     const int grid = n_tiles < MINB * L.num_sms ? n_tiles : MINB * L.num_sms;
-    sor_blocked_tma_kernel<R, NW, MINB><<<grid, 32 * NW, smem, L.stream>>>(p_map, d_map, a, ntx, nty, work_counter);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(32 * NW);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = L.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this launch with the previous pass's tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, sor_blocked_tma_kernel<R, NW, MINB>, p_map, d_map, a, ntx, nty, work_counter);
     ++*L.launches;
-    return (int)cudaGetLastError();
+    return (int)e;
 }
 
 template <int R, int NW, int MINB>
