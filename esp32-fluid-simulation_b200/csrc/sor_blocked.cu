@@ -263,11 +263,10 @@ sor_blocked_tma_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_c
     const uint32_t tx_bytes = (has_p ? 2u : 1u) * RH * BLK_RW * 4u;
     const int n_tiles = ntx * nty;
 
-    // thread 0: claim the next tile (dynamic: wall tiles cost more than interior ones) and start
-    // its bulk-tensor loads
-    auto claim_and_prefetch = [&](int slot) {
-        const int idx = atomicAdd(work_counter, 1);
-        s_tile[slot] = idx;
+    // thread 0: tiles are claimed dynamically (wall tiles cost more than interior ones) TWO ahead:
+    // the ticket used for a prefetch was drawn one tile earlier, so the atomic's L2 round trip
+    // (~1 us) is never waited for in front of the tile's first barrier.
+    auto prefetch = [&](int idx) {
         if (idx < n_tiles) {
             int tx, ty;
             tile_coords(idx, ntx, nty, tx, ty);
@@ -285,7 +284,13 @@ sor_blocked_tma_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_c
     // Programmatic dependent launch: this grid may have been scheduled while the previous pass was
     // still draining; everything above overlapped with it, nothing below may (p_in is its output).
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (threadIdx.x == 0) claim_and_prefetch(0);
+    int ahead = n_tiles;                       // thread 0 only: the ticket drawn one tile early
+    if (threadIdx.x == 0) {
+        const int first = atomicAdd(work_counter, 1);
+        s_tile[0] = first;
+        prefetch(first);
+        ahead = atomicAdd(work_counter, 1);
+    }
     __syncthreads();
     uint32_t phase = 0;
     for (int it = 0;; it++) {
@@ -316,7 +321,11 @@ sor_blocked_tma_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_c
             }
         }
         __syncthreads();                       // every warp has drained the staging buffers
-        if (threadIdx.x == 0) claim_and_prefetch((it + 1) & 1);   // visible after sweep_pass's first barrier
+        if (threadIdx.x == 0) {
+            s_tile[(it + 1) & 1] = ahead;      // visible after sweep_pass's first barrier
+            prefetch(ahead);
+            ahead = atomicAdd(work_counter, 1);   // consumed one tile later
+        }
         if (!region_hits_wall<R, NW>(a, rlx0, rly0)) sweep_pass<R, NW, false>(p, dxd, a, mail, gi0, gj0, a.n_half);
         else                                          sweep_pass<R, NW, true>(p, dxd, a, mail, gi0, gj0, a.n_half);
         store_tile<R>(p, a, a.p_out, rlx0, rly0, lx0, ly0);
