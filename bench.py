@@ -241,18 +241,26 @@ def bench_single(args, fb, synth, torch):
     sor_ms = s0.elapsed_time(s1) / reps
     peak, peak_src = measured_peaks()
     achieved = SOR_BYTES_PER_NODE_ITER * nodes * ITERS / (sor_ms * 1e-3) / 1e9
-    traffic = None
+    # `traffic`: ncu dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per LAUNCH
+    # (profiles/sor_traffic.json, from profiles/r01_ncu_sor_blocked_tma_final.json)
+    traffic = traffic_solve = None
     tpath = os.path.join(ROOT, "profiles", "sor_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_solve")
+            tj = json.load(open(tpath))
+            traffic, traffic_solve = tj.get("dram_bytes_per_pass"), tj.get("dram_bytes_per_solve")
         except Exception:
-            traffic = None
+            traffic = traffic_solve = None
+    alg_launch = SOR_BYTES_PER_NODE_ITER * nodes * ITERS / max(sor_launches, 1)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src,
-        "kernel": "SOR pressure solve (fs_poisson_solve: 50 red-black iterations, all launches of one solve)",
-        "algorithmic_bytes": SOR_BYTES_PER_NODE_ITER * nodes * ITERS,
+        "kernel": "sor_blocked_tma_kernel: one launch = one pass of the SOR solve = up to 8 fused red-black "
+                  "iterations over the whole grid (fs_poisson_solve, K=50 => 7 launches)",
+        "algorithmic_bytes_per_launch": alg_launch, "avg_launch_ms": sor_ms / max(sor_launches, 1),
+        "algorithmic_bytes_per_solve": SOR_BYTES_PER_NODE_ITER * nodes * ITERS, "traffic_per_solve": traffic_solve,
+        "note": "achieved = 12 B/node-iteration (SURVEY 8d) x nodes x iterations per launch / average launch time; "
+                "frac > 1 because temporal blocking moves ~1/8 of those bytes (see traffic)",
         "ms": sor_ms, "launches_per_solve": sor_launches,
         "gnode_iters_per_s": nodes * ITERS / (sor_ms * 1e-3) / 1e9,
         "step_frac": (STEP_BYTES_PER_NODE * nodes / (ms * 1e-3) / 1e9) / peak,

@@ -81,3 +81,70 @@ def test_multi_gpu_decomposed_run_matches_oracle(oracle, tmp_path, world, mode, 
     assert_bit_equal(gv, ov, f"velocity ({mode}, {world} GPUs)")
     assert_bit_equal(gc, oc, f"dye ({mode}, {world} GPUs)")
     assert_bit_equal(gp, op, f"pressure ({mode}, {world} GPUs)")
+
+
+# ---- BASELINE-scale property: the decomposition must not change a bit ---------------------------
+
+def _scale_worker(rank, world, port, tile, iters, steps, out_dir):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch
+    import torch.distributed as dist
+
+    import esp32_fluid_simulation_b200 as fb
+    from esp32_fluid_simulation_b200 import synth
+    from esp32_fluid_simulation_b200.dist import (ArenaTileOps, DecomposedSim, Decomposition, PeerComm,
+                                                  max_window_nodes, process_grid)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=dev)
+    try:
+        px, py = process_grid(world)
+        gx, gy = tile * px, tile * py
+        # every rank builds the SAME global field on its own GPU (same seed, same generator)
+        g = torch.Generator(device=dev).manual_seed(1234)
+        v = (torch.rand(gy, gx, 2, device=dev, generator=g) - 0.5) * 120.0
+        c = torch.randint(0, 2 ** 31 - 1, (gy, gx, 3), device=dev, dtype=torch.int32, generator=g)
+        drags = [synth.drags(gx, gy, s, n=16) for s in range(steps)]
+        ghost = 64
+        dec = Decomposition(gx, gy, world, rank, ghost=ghost)
+        ops = ArenaTileOps(rank, max_window_nodes(gx, gy, world, ghost))
+        sim = DecomposedSim(dec, ops, PeerComm(ops, world, rank, gx, gy, ghost), iters, 8, DT, static_halo=48)
+        w = dec.window
+        sim.v.copy_(v[w.oy:w.oy + w.ny, w.ox:w.ox + w.nx])
+        sim.c.copy_(c[w.oy:w.oy + w.ny, w.ox:w.ox + w.nx])
+        for s in range(steps):
+            sim.step(drags[s])
+        torch.cuda.synchronize()
+        sim.check()
+        # ... and the whole grid on this GPU alone, through the single-GPU entry point
+        ctx = fb.Context(rank)
+        for s in range(steps):
+            ctx.step(v, c, drags[s], gx, gy, DT, 1.0, iters, 1.96)
+        ctx.synchronize()
+        same_v = torch.equal(sim.v[w.y0:w.y1, w.x0:w.x1].view(torch.int32),
+                             v[dec.gy0:dec.gy1, dec.gx0:dec.gx1].view(torch.int32))
+        same_c = torch.equal(sim.c[w.y0:w.y1, w.x0:w.x1], c[dec.gy0:dec.gy1, dec.gx0:dec.gx1])
+        with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+            f.write(f"{int(same_v)} {int(same_c)} {gx} {gy}\n")
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_one_gpu_equals_n_gpus_at_baseline_scale(tmp_path):
+    """4096^2 nodes per GPU, K=50 (bench.py's weak-scaling workload; 8192x16384 on 8 GPUs): every rank
+    compares its rectangle of the decomposed run with the same grid stepped on one GPU — bit for bit.
+    (The single-GPU path is oracle-checked at 4096^2 in test_gpu_parity.py.)"""
+    world = min(_n_gpus(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 8 if world >= 8 else 4 if world >= 4 else 2
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_scale_worker, args=(world, port, 4096, 50, 2, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        same_v, same_c, gx, gy = (tmp_path / f"rank{r}.txt").read_text().split()
+        assert same_v == "1" and same_c == "1", f"rank {r} differs from the single-GPU run on {gx}x{gy}"
