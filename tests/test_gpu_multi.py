@@ -55,20 +55,37 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
+def _spawn_bounded(fn, args, nprocs, limit_s=300):
+    """mp.spawn with a deadline: if a rank dies, its neighbours would spin in halo_exchange_kernel
+    waiting for its flags — kill everything instead of hanging the box."""
+    import time
+
+    import torch.multiprocessing as mp
+    ctx = mp.spawn(fn, args=args, nprocs=nprocs, join=False)
+    deadline = time.time() + limit_s
+    try:
+        while not ctx.join(timeout=5):
+            if time.time() > deadline:
+                raise TimeoutError(f"multi-GPU ranks still running after {limit_s} s")
+    except BaseException:
+        for p in ctx.processes:
+            if p.is_alive():
+                p.kill()
+        raise
+
+
 @pytest.mark.parametrize("mode,static_halo", [("peer", None), ("peer", 24), ("nccl", None)])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_multi_gpu_decomposed_run_matches_oracle(oracle, tmp_path, world, mode, static_halo):
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
-    import torch.multiprocessing as mp
-
     from esp32_fluid_simulation_b200 import synth
     gx, gy, iters, sor_t, ghost, steps = 1024, 768, 20, 6, 32, 3
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(world, port, gx, gy, iters, sor_t, ghost, steps, mode, static_halo, str(tmp_path)),
-             nprocs=world, join=True)
+    _spawn_bounded(_worker, (world, port, gx, gy, iters, sor_t, ghost, steps, mode, static_halo, str(tmp_path)),
+                   world)
     ov, oc = synth.velocity(gx, gy, vmax=150.0), synth.dye(gx, gy)
     for s in range(steps):
         ov, oc, op, od = oracle.step(ov, oc, synth.drags(gx, gy, s, n=8, vmax=400.0), DT, 1.0, iters, 1.96,
@@ -140,11 +157,10 @@ def test_one_gpu_equals_n_gpus_at_baseline_scale(tmp_path):
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 8 if world >= 8 else 4 if world >= 4 else 2
-    import torch.multiprocessing as mp
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_scale_worker, args=(world, port, 4096, 50, 2, str(tmp_path)), nprocs=world, join=True)
+    _spawn_bounded(_scale_worker, (world, port, 4096, 50, 2, str(tmp_path)), world)
     for r in range(world):
         same_v, same_c, gx, gy = (tmp_path / f"rank{r}.txt").read_text().split()
         assert same_v == "1" and same_c == "1", f"rank {r} differs from the single-GPU run on {gx}x{gy}"
