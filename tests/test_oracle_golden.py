@@ -160,3 +160,48 @@ def test_color_wheel_shape(oracle):
     assert not v.any()
     assert c.max() == 0xFFFFFFFF and c.shape == (81, 61, 3)
     assert (c.sum(axis=2, dtype=np.uint64) > 0).all()
+
+
+def _upscale_numpy(c):
+    """Second, independent restatement of ino:116-177 (vectorised float32 numpy) to cross-check the C
+    oracle: the draw routine lives in the .ino and cannot be compiled off-device, so this arithmetic is
+    pinned by two restatements rather than by reference code."""
+    f32 = np.float32
+    c = c.astype(np.float32)                                   # UQ32 -> float, uq32.h:15
+    dim_y, dim_x = c.shape[:2]
+    c11, c21 = c[:-1, :-1], c[:-1, 1:]                          # (i, j), (i+1, j)   [array index = (j, i)]
+    c12, c22 = c[1:, :-1], c[1:, 1:]                            # (i, j+1), (i+1, j+1)
+    quarter = f32(0.25)
+
+    def ramp(a, b):                                             # c, c+=dc, ... accumulated (ino:133-152)
+        d = (b - a) * quarter
+        out = [a]
+        for _ in range(3):
+            out.append(out[-1] + d)
+        return out
+
+    left, right = ramp(c11, c21), ramp(c12, c22)                # 4 sub-rows ii along the fast axis i
+    img = np.zeros(((dim_x - 1) * 4, (dim_y - 1) * 4), np.uint16)
+    for ii in range(4):
+        a, b = left[ii], right[ii]
+        d = (b - a) * quarter                                   # ino:157
+        vals = [a]
+        for _ in range(3):
+            vals.append(vals[-1] + d)                           # ino:160
+        for jj in range(4):
+            q = vals[jj] + f32(0.5)                             # uq32.h:13
+            raw = np.where(q >= f32(4294967296.0), np.uint64(0xFFFFFFFF), q.astype(np.uint64)).astype(np.uint64)
+            w = ((raw[..., 0] & 0xF8000000) >> 16) | ((raw[..., 1] & 0xFC000000) >> 21) | ((raw[..., 2] & 0xF8000000) >> 27)
+            w = w.astype(np.uint16)
+            w = ((w << 8) | (w >> 8)).astype(np.uint16)        # bswap16, ino:173
+            img[ii::4, jj::4] = w.T                            # image row = 4i+ii, column = 4j+jj
+    return img
+
+
+@pytest.mark.parametrize("shape", [(2, 2), (5, 4), (61, 81), (33, 100)])
+def test_upscale_oracle_matches_independent_numpy_restatement(oracle, shape):
+    dim_x, dim_y = shape
+    rng = np.random.default_rng(31)
+    c = rng.integers(0, 2 ** 32, (dim_y, dim_x, 3), dtype=np.uint32)
+    c[0, 0] = 0xFFFFFFFF                                       # saturating corner
+    assert np.array_equal(oracle.upscale4_rgb565(c), _upscale_numpy(c))
