@@ -155,6 +155,18 @@ def run_reference_arm(args):
 # B200 arm
 # ---------------------------------------------------------------------------------------------
 
+def start_watchdog(seconds: float):
+    """Multi-rank runs only: if a rank dies, its neighbours spin in halo_exchange_kernel waiting for its
+    flags.  Exit hard (which tears the CUDA context down and kills the kernel) instead of hanging."""
+    def fire():
+        print(f"[bench] watchdog: no result after {seconds:.0f} s, aborting", file=sys.stderr, flush=True)
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -175,6 +187,7 @@ def run_b200_arm(args):
     if world > 1:
         from esp32_fluid_simulation_b200 import dist as fdist
         args.clock_sampler = ClockSampler
+        watchdog = start_watchdog(float(os.environ.get("FS_BENCH_WATCHDOG_S", "900")))
         result = fdist.bench_decomposed(args, GRID, args.iters, N_DRAGS)
     else:
         result = bench_single(args, fb, synth, torch)
@@ -182,6 +195,7 @@ def run_b200_arm(args):
         print(json.dumps(result), flush=True)
     if world > 1:
         dist.barrier()
+        watchdog.cancel()
         dist.destroy_process_group()
 
 
