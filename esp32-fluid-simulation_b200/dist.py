@@ -145,9 +145,11 @@ class DecomposedSim:
                  dt=np.float32(1 / 30.0), dx=np.float32(1.0), omega=np.float32(1.96),
                  static_halo: int | None = None):
         """static_halo: exchange this many nodes for the advects instead of agreeing on the step's
-        max displacement (saves one all-reduce + host sync per step).  A backtrace that goes further
-        raises the device status flag, which `check()` reads: the run is then invalid — use a larger
-        halo/ghost.  None = size every advect halo exactly (always correct, one host sync per step)."""
+        max displacement (saves one all-reduce + host sync per step).  The kernels raise the device
+        status flag (read by `check()`) when a backtrace leaves the WINDOW, so detection is airtight
+        only for static_halo == ghost; with a narrower static halo, backtraces between the two widths
+        would read stale ghosts unnoticed.  None = size every advect halo exactly (always correct, one
+        host sync per step)."""
         self.dec, self.ops, self.comm = dec, ops, comm
         self.static_halo = static_halo
         if static_halo is not None and dec.world > 1 and static_halo > dec.ghost:
@@ -486,7 +488,9 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
                       file=sys.stderr, flush=True)
             mode, ops, comm = "nccl", None, None
     if mode == "peer":
-        static_halo = 48     # covers the 34-node backtraces of the +-1000 nodes/s synthetic drags
+        static_halo = ghost  # refresh the WHOLE ghost every time: a backtrace is then either served from fresh
+                             # data or leaves the window and raises the overrun flag (the +-1000 nodes/s
+                             # synthetic drags move a node 34 cells; ghost = 64)
     else:
         ops = CudaTileOps(local_rank)
         comm = TorchComm(dev)
