@@ -31,11 +31,19 @@ class OracleTileOps:
     def download(self, t):
         return self._np(t).copy()
 
-    def tile_advect(self, next_p, p, vel, w, dt, no_slip):
-        self.overrun = self.o.tile_advect(self._np(next_p), self._np(p), self._np(vel), w, dt, no_slip)
-
     def tile_check(self):
         assert not getattr(self, "overrun", False), "advect backtrace left the window"
+
+    def tile_advect(self, next_p, p, vel, w, dt, no_slip):
+        hit = self.o.tile_advect(self._np(next_p), self._np(p), self._np(vel), w, dt, no_slip)
+        self.overrun = hit
+        self.overrun_sticky = getattr(self, "overrun_sticky", False) or hit
+
+    def tile_check_now(self):
+        """Same contract as fs_tile_check: report (and clear) any overrun since the last check."""
+        hit, self.overrun_sticky = getattr(self, "overrun_sticky", False), False
+        if hit:
+            raise RuntimeError("advect backtrace left the window (FS_ERR_HALO_OVERRUN)")
 
     def tile_apply_drags(self, v, drags, w):
         self.o.tile_apply_drags(self._np(v), drags, w)

@@ -97,6 +97,48 @@ def test_halo_wider_than_ghost_is_an_error(oracle):
         run_threaded(world, make, 1, lambda s: None)
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_static_full_ghost_halo_needs_no_agreement_and_detects_overruns(oracle, world):
+    """static_halo == ghost: no per-step all-reduce, still bit-identical; and a backtrace that leaves the
+    window is reported by check() instead of passing silently."""
+    from esp32_fluid_simulation_b200.dist import DecomposedSim, Decomposition
+    gx, gy, iters, sor_t, ghost, steps = 64, 64, 6, 2, 16, 3
+    v0, c0 = _inputs(gx, gy, 5, 60.0)                  # <= 2 nodes per step, drags below add <= 10
+
+    def run(vfield, expect_overrun):
+        calls = []
+
+        def make(rank, comm):
+            dec = Decomposition(gx, gy, world, rank, ghost=ghost)
+            comm_all_max = comm.all_max
+            comm.all_max = lambda v: calls.append(v) or comm_all_max(v)
+            sim = DecomposedSim(dec, OracleTileOps(oracle), comm, iters, sor_t, DT, static_halo=ghost)
+            w = dec.window
+            sim.load(vfield[w.oy:w.oy + w.ny, w.ox:w.ox + w.nx], c0[w.oy:w.oy + w.ny, w.ox:w.ox + w.nx])
+            return sim
+
+        sims = run_threaded(world, make, steps, lambda s: _drags(gx, gy, s))
+        assert not calls, "static halo must not all-reduce"
+        hits = 0
+        for sim in sims:
+            try:
+                sim.check()
+            except RuntimeError:
+                hits += 1
+        assert (hits > 0) == expect_overrun
+        return sims
+
+    sims = run(v0, expect_overrun=False)
+    ov, oc = v0.copy(), c0.copy()
+    for s in range(steps):
+        ov, oc = oracle.step(ov, oc, _drags(gx, gy, s), DT, 1.0, iters, 1.96)
+    assert_bit_equal(gather_owned(sims, "v", gx, gy, 2, np.float32), ov, "velocity")
+    assert_bit_equal(gather_owned(sims, "c", gx, gy, 3, np.uint32), oc, "dye")
+    fast = v0.copy()
+    fast[gy // 2, :, 1] = 1500.0                       # 50 nodes per step across the cut between ranks
+    run(fast, expect_overrun=True)
+
+
 def _gloo_worker(rank, world, port, gx, gy, out_dir):
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
