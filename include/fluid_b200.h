@@ -60,12 +60,13 @@ int  fs_ctx_create(fs_ctx **out, int device, void *stream);
 int  fs_ctx_destroy(fs_ctx *ctx);
 int  fs_ctx_synchronize(fs_ctx *ctx);
 /* Kernel-variant switches for A/B measurement (all variants are bit-identical):
- *   "sor"    : 0 = one half-sweep per launch, 1 = shared-memory temporally blocked (default)
+ *   "sor"    : 0 = one half-sweep per launch, 1 = temporally blocked in registers + shared memory (default)
  *   "sor_t"  : full iterations fused per HBM round trip (1..8, default 8)
  *   "sor_shape": CTA region and loader of the blocked solver: 0 = 128x96 nodes, 1 = 128x192, both
  *              loaded straight from global; 2 / 3 = the same regions with persistent CTAs whose
  *              next tile is prefetched by TMA (3 is the default; falls back to 1 when rows are
- *              not 16-byte multiples)
+ *              not 16-byte multiples); 4 / 5 / 6 = TMA variants with 12x12, 16x10, 12x16
+ *              (warps x rows per warp) strips
  *   "sor_one_launch": 1 = all passes of a solve run in ONE persistent launch with tile-level
  *              dependencies between passes (shapes 2, 3, 5); 0 (default) = one launch per pass.
  *              Measured: the dependency probes and release fences on the issuing thread cost more
