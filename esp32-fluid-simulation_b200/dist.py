@@ -389,6 +389,11 @@ class PeerComm:
     def __init__(self, ops: ArenaTileOps, world: int, rank: int, gdim_x: int, gdim_y: int, ghost: int,
                  grid=None, peer_bases: dict | None = None, handles: list | None = None):
         self.ops, self.rank, self.world = ops, rank, world
+        if ops.ctx.get_option("sor") != 1:
+            # the one-launch-per-half-sweep solver seeds and relaxes the rectangle grown by H inside
+            # p_out, i.e. it WRITES ghost cells; a neighbour's strip that was stored early would be lost
+            raise ValueError("peer-memory halos need the blocked SOR kernel (option sor=1): it is the "
+                             "only solver that never writes ghost cells")
         self.decs = [Decomposition(gdim_x, gdim_y, world, r, ghost, grid) for r in range(world)]
         self.seq = 0
         me = self.decs[rank]

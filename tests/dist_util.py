@@ -126,3 +126,130 @@ def gather_owned(sims, field_name, gdim_x, gdim_y, channels, dtype):
         d = sim.dec
         out[d.gy0:d.gy1, d.gx0:d.gx1] = sim.owned(getattr(sim, field_name))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# One-sided emulation of the peer-memory halo protocol (csrc/halo.cu) on CPU threads.
+#
+# ThreadComm above has two-sided semantics: data lands in the receiver's ghosts when the RECEIVER
+# reaches the exchange.  The real PeerComm is one-sided: a rank stores its strips straight into the
+# neighbour's window the moment IT reaches the exchange, then signals a flag and waits for the
+# neighbours' flags.  A neighbour that is still busy with earlier kernels gets its ghosts overwritten
+# under its feet — harmless only if the step sequence never has it reading (or later rewriting) those
+# cells at that point.  This emulation reproduces exactly that, and lets a test slow individual ranks
+# down to provoke every "neighbour runs ahead" ordering.
+# ---------------------------------------------------------------------------------------------------
+
+class OneSidedWorld:
+    def __init__(self, world, slow=None, jitter=0.0, seed=0):
+        import random
+        self.world = world
+        self.ops = [None] * world                     # rank -> OneSidedOps (registers its buffers)
+        self.flags = [dict() for _ in range(world)]   # rank -> {direction: last sequence number seen}
+        self.cv = threading.Condition()
+        self.slow = slow or {}                        # rank -> seconds of delay before every compute op
+        self.jitter, self.rng = jitter, random.Random(seed)
+        self.failed = False
+
+    def pause(self, rank):
+        d = self.slow.get(rank, 0.0)
+        if self.jitter:
+            with self.cv:
+                d += self.rng.random() * self.jitter
+        if d:
+            import time
+            time.sleep(d)
+
+
+class OneSidedOps(OracleTileOps):
+    """OracleTileOps whose buffers are registered by creation order (= the arena offset of the real
+    implementation, identical on every rank) and whose compute ops can be delayed."""
+
+    def __init__(self, oracle, world: OneSidedWorld, rank: int):
+        super().__init__(oracle)
+        self.w, self.rank, self.bufs = world, rank, []
+        world.ops[rank] = self
+
+    def empty(self, shape, dtype):
+        t = super().empty(shape, dtype)
+        self.bufs.append(t)
+        return t
+
+    def key(self, tensor):
+        for k, b in enumerate(self.bufs):
+            if b is tensor:
+                return k
+        raise KeyError("field is not an arena buffer")
+
+    def _delayed(name):
+        def f(self, *a, **kw):
+            self.w.pause(self.rank)
+            return getattr(OracleTileOps, name)(self, *a, **kw)
+        return f
+
+    tile_advect = _delayed("tile_advect")
+    tile_apply_drags = _delayed("tile_apply_drags")
+    tile_calculate_divergence = _delayed("tile_calculate_divergence")
+    tile_subtract_gradient = _delayed("tile_subtract_gradient")
+
+    def tile_sor_sweeps(self, p_out, p_in, div, w, dx, omega, first_parity, n_half):
+        """Same WRITE SET as the CUDA blocked kernel: only the compute rectangle of p_out is written.
+        (The oracle's window sweep seeds and relaxes the rectangle grown by n_half inside p_out, i.e. it
+        writes ghost cells — fine for two-sided exchanges, fatal for one-sided ones: a neighbour's strip
+        that arrived early would be overwritten.  The peer path therefore requires the blocked kernel.)"""
+        self.w.pause(self.rank)
+        tmp = torch.zeros_like(p_out)
+        OracleTileOps.tile_sor_sweeps(self, tmp, p_in, div, w, dx, omega, first_parity, n_half)
+        p_out[w.y0:w.y1, w.x0:w.x1] = tmp[w.y0:w.y1, w.x0:w.x1]
+
+
+class OneSidedComm:
+    def __init__(self, world: OneSidedWorld, rank: int, decs):
+        self.w, self.rank, self.decs, self.seq = world, rank, decs, 0
+
+    def exchange_fields(self, dec, fields, width):
+        ops = self.w.ops[self.rank]
+        self.seq += 1
+        for peer, dx, dy in dec.neighbours():
+            ys, xs = dec.send_slices(dx, dy, width)
+            yr, xr = self.decs[peer].recv_slices(-dx, -dy, width)
+            for f in fields:
+                # the store into the neighbour's window happens NOW, whatever the neighbour is doing
+                self.w.ops[peer].bufs[ops.key(f)][yr, xr] = f[ys, xs].clone()
+            with self.w.cv:
+                self.w.flags[peer][(-dx, -dy)] = self.seq
+                self.w.cv.notify_all()
+        with self.w.cv:
+            for _, dx, dy in dec.neighbours():
+                if not self.w.cv.wait_for(lambda: self.w.flags[self.rank].get((dx, dy), 0) >= self.seq or self.w.failed,
+                                          timeout=120):
+                    raise TimeoutError("halo flag never arrived")
+                if self.w.failed:
+                    raise RuntimeError("another rank failed")
+
+    def all_max(self, value):
+        raise AssertionError("the one-sided protocol is used with a static halo: no all-reduce")
+
+
+def run_one_sided(world, make_sim, n_steps, drags_for_step, osw: OneSidedWorld):
+    sims = [make_sim(r) for r in range(world)]
+    errors = []
+
+    def body(sim):
+        try:
+            for s in range(n_steps):
+                sim.step(drags_for_step(s))
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            with osw.cv:
+                osw.failed = True
+                osw.cv.notify_all()
+
+    threads = [threading.Thread(target=body, args=(s,)) for s in sims]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return sims

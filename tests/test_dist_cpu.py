@@ -181,3 +181,35 @@ def test_two_process_gloo_group(oracle, tmp_path):
         gv[y0:y1, x0:x1], gc[y0:y1, x0:x1] = z["v"], z["c"]
     assert_bit_equal(gv, ov, "velocity (gloo)")
     assert_bit_equal(gc, oc, "dye (gloo)")
+
+
+@pytest.mark.parametrize("schedule", ["even", "rank0-slow", "last-slow", "alternate-slow", "jitter"])
+@pytest.mark.parametrize("world,iters,sor_t", [(2, 6, 2), (4, 7, 3), (8, 4, 4)])
+def test_one_sided_halo_protocol_is_schedule_independent(oracle, world, iters, sor_t, schedule):
+    """The peer-memory exchange (csrc/halo.cu) stores into the neighbours' windows at the SENDER's
+    program point.  Emulated here with threads; ranks are slowed down to let neighbours run ahead as far
+    as the flags allow.  Whatever the schedule, the result must be the whole-grid oracle's, bit for bit —
+    i.e. no step of the sequence reads or rewrites ghosts that a neighbour may already be overwriting."""
+    from dist_util import OneSidedComm, OneSidedOps, OneSidedWorld, run_one_sided
+    from esp32_fluid_simulation_b200.dist import DecomposedSim, Decomposition
+    gx, gy, ghost, steps = (48, 64, 16, 3) if world == 2 else (64, 64, 16, 3) if world == 4 else (64, 128, 16, 2)
+    v0, c0 = _inputs(gx, gy, 40 + world, 60.0)
+    slow = {"even": {}, "rank0-slow": {0: 0.004}, "last-slow": {world - 1: 0.004},
+            "alternate-slow": {r: 0.003 for r in range(0, world, 2)}, "jitter": {}}[schedule]
+    osw = OneSidedWorld(world, slow=slow, jitter=0.003 if schedule == "jitter" else 0.0, seed=world)
+    decs = [Decomposition(gx, gy, world, r, ghost=ghost) for r in range(world)]
+
+    def make(rank):
+        sim = DecomposedSim(decs[rank], OneSidedOps(oracle, osw, rank), OneSidedComm(osw, rank, decs), iters, sor_t,
+                            DT, static_halo=ghost)
+        w = decs[rank].window
+        sim.load(v0[w.oy:w.oy + w.ny, w.ox:w.ox + w.nx], c0[w.oy:w.oy + w.ny, w.ox:w.ox + w.nx])
+        return sim
+
+    sims = run_one_sided(world, make, steps, lambda s: _drags(gx, gy, s, n=4), osw)
+    ov, oc = v0.copy(), c0.copy()
+    for s in range(steps):
+        ov, oc, op, od = oracle.step(ov, oc, _drags(gx, gy, s, n=4), DT, 1.0, iters, 1.96, want_fields=True)
+    assert_bit_equal(gather_owned(sims, "v", gx, gy, 2, np.float32), ov, "velocity")
+    assert_bit_equal(gather_owned(sims, "c", gx, gy, 3, np.uint32), oc, "dye")
+    assert_bit_equal(gather_owned(sims, "p_last", gx, gy, 0, np.float32), op, "pressure")
