@@ -77,3 +77,17 @@ def test_no_contracted_packed_fma_in_sass(built):
     assert " FFMA2 " not in sass
     fused = [l for l in sass.splitlines() if " FFMA " in l or " FFMA." in l]
     assert not fused, fused[:5]
+
+
+def test_header_is_valid_c99_and_layouts_match_the_reference(tmp_path):
+    """The boundary is a C ABI: the header must compile as plain C, and the POD layouts must be the
+    reference's (Vector2<float> 8 B, Vector3<UQ32> 12 B, struct drag 12 B)."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "fluid_b200.h"\n'
+                   'int main(void){ fs_tile t; fs_halo_copy h; (void)t; (void)h;\n'
+                   '  return sizeof(fs_vec2f)==8 && sizeof(fs_rgb_uq32)==12 && sizeof(fs_drag)==12 ? 0 : 1; }\n')
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
