@@ -97,6 +97,79 @@ def drags(dim_x, dim_y, step, n=16, seed=0xD4A6, vmax=1000.0) -> np.ndarray:
     return out
 
 
+# ---------------------------------------------------------------------------------------------
+# The reference's own inputs, restated host-side: they run on the MCU's CPU in the
+# reference too and are not part of the hot path.
+# ---------------------------------------------------------------------------------------------
+
+def _uq32(x: np.ndarray) -> np.ndarray:
+    """UQ32(float), uq32.h:13, saturating like the CUDA path."""
+    y = x.astype(np.float32) + np.float32(0.5)
+    return np.where(y >= np.float32(4294967296.0), np.uint64(0xFFFFFFFF),
+                    np.maximum(y, 0).astype(np.uint64)).astype(np.uint32)
+
+
+def color_wheel(dim_x: int, dim_y: int):
+    """setup(), ino:196-241: zero velocity; three-sector colour wheel (atan2f of the node's offset from
+    the centre, sectors split at +-pi/3); then two IN-PLACE 1-2-1 smoothing passes, first along j, then
+    along i, each walked in index order so the lower-index neighbour is already smoothed.  Returns
+    (velocity float32[dim_y, dim_x, 2], dye uint32[dim_y, dim_x, 3]) in the reference layout
+    (dim_x = N_ROWS is the fast axis)."""
+    f32 = np.float32
+    i = np.arange(dim_x, dtype=np.int64)[None, :]
+    j = np.arange(dim_y, dtype=np.int64)[:, None]
+    ang = np.arctan2((-(i - dim_x // 2)).astype(f32), (j - dim_y // 2).astype(f32)).astype(np.float64)
+    third = 3.1415926535897932384626433832795 / 3
+    full = _uq32(np.array([4294967295.0], f32))[0]               # Vector3<float>(UINT32_MAX, ...) -> UQ32
+    c = np.zeros((dim_y, dim_x, 3), np.uint32)
+    red, green = ang < -third, (ang >= -third) & (ang < third)
+    c[..., 0][red] = full
+    c[..., 1][green] = full
+    c[..., 2][~(red | green)] = full
+    q, h = f32(0.25), f32(0.5)
+    for jj in range(dim_y):                                      # ino:220-230 (sequential in j)
+        mid = c[jj].astype(f32)
+        lo = c[jj - 1].astype(f32) if jj > 0 else mid
+        hi = c[jj + 1].astype(f32) if jj < dim_y - 1 else mid
+        c[jj] = _uq32(q * lo + h * mid + q * hi)
+    for ii in range(dim_x):                                      # ino:231-241 (sequential in i)
+        mid = c[:, ii].astype(f32)
+        lo = c[:, ii - 1].astype(f32) if ii > 0 else mid
+        hi = c[:, ii + 1].astype(f32) if ii < dim_x - 1 else mid
+        c[:, ii] = _uq32(q * lo + h * mid + q * hi)
+    return np.zeros((dim_y, dim_x, 2), np.float32), c
+
+
+def arduino_map(x: int, in_min: int, in_max: int, out_min: int, out_max: int) -> int:
+    """Arduino map(): long arithmetic, division truncating toward zero."""
+    num = (x - in_min) * (out_max - out_min)
+    den = in_max - in_min
+    quo = abs(num) // abs(den)
+    return (quo if (num >= 0) == (den > 0) else -quo) + out_min
+
+
+def touch_drags(samples, n_rows: int, n_cols: int, polling_ms: int = 10,
+                cal=(200, 3700, 240, 3800)) -> np.ndarray:
+    """touch_routine(), ino:63-96: `samples` is one (touched, raw_x, raw_y) per polling period.  Every
+    touched sample that follows a touched sample yields a drag record {coords, velocity} with
+    coords = map() of the raw reading onto [0, N_COLS] x [0, N_ROWS] (ino:77-78; the upper bound is
+    inclusive in the reference — such records fall outside the grid and fs_apply_drags drops them) and
+    velocity = delta_coords * 1000.f / POLLING_PERIOD nodes/s (ino:82-83).  Queue depth / dropping
+    (ino:49,85) is the caller's business."""
+    out, last, last_touched = [], None, False
+    for touched, rx, ry in samples:
+        if touched:
+            cx = arduino_map(int(rx), cal[0], cal[1], 0, n_cols)
+            cy = arduino_map(int(ry), cal[2], cal[3], 0, n_rows)
+            if last_touched:
+                vx = np.float32(np.float32(cx - last[0]) * np.float32(1000.0)) / np.float32(polling_ms)
+                vy = np.float32(np.float32(cy - last[1]) * np.float32(1000.0)) / np.float32(polling_ms)
+                out.append((cx & 0xFFFF, cy & 0xFFFF, vx, vy))
+            last = (cx, cy)
+        last_touched = bool(touched)
+    return np.array(out, DRAG_DTYPE) if out else np.zeros(0, DRAG_DTYPE)
+
+
 def fnv1a64(a: np.ndarray) -> int:
     """FNV-1a-64 over the raw bytes (small arrays only; pure Python loop)."""
     h = 0xcbf29ce484222325
