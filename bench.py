@@ -129,20 +129,34 @@ def cpu_step_rate(dim_x, dim_y, steps, warmup):
     return dim_x * dim_y * len(times) / total / 1e6, total / len(times), kind
 
 
+def pin_to_one_core():
+    """The reference is single-threaded; keep it on one core so the scheduler does not migrate it."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        os.sched_setaffinity(0, {cores[len(cores) // 2]})
+        return cores[len(cores) // 2]
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: a 4096 x 512 slab of the 4096^2 workload per step (~0.7 s of CPU each)
-    dim_x, dim_y = GRID, 512
-    rate, sec, kind = cpu_step_rate(dim_x, dim_y, args.steps, args.warmup)
-    sample = (f"each step = one full loop() body on a {dim_x}x{dim_y} slab of the {GRID}x{GRID} grid, "
-              f"K={ITERS}, {N_DRAGS} drags; single thread (the reference is single-threaded)")
+    # the SAME config as the B200 arm: every step is one full loop() body on the whole 4096^2 grid
+    # (~4 s of CPU each; the driver's --steps 20 --warmup 3 is ~90 s).  Bounded: at most 25 timed steps.
+    dim_x, dim_y = GRID, GRID
+    core = pin_to_one_core()
+    steps, warmup = max(1, min(args.steps, 25)), max(0, min(args.warmup, 3))
+    rate, sec, kind = cpu_step_rate(dim_x, dim_y, steps, warmup)
+    sample = (f"{steps} timed + {warmup} warm-up full loop() bodies on the whole {dim_x}x{dim_y} grid, "
+              f"K={ITERS}, {N_DRAGS} drags; single thread pinned to core {core} (the reference is single-threaded)")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+uq32", "data": "synthetic",
         "config": {"workload": f"single {GRID}x{GRID} grid, {ITERS} SOR iterations, velocity + dye advection",
+                   "grid": [dim_x, dim_y], "sor_iters": ITERS, "drags_per_step": N_DRAGS, "same_config": True,
                    "sample": sample},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -211,8 +225,13 @@ def bench_single(args, fb, synth, torch):
         dc = torch.from_numpy(c0.view(np.int32)).cuda()
     stream.synchronize()
 
+    with torch.cuda.stream(stream):
+        dc2 = torch.empty_like(dc)
+    dyes = [dc, dc2]
+
     def step(s):
-        ctx.step(dv, dc, drags[s], n, n, synth.DT, synth.DX, ITERS, synth.OMEGA)
+        # loop() swaps the dye pointers (ino:286): c_in -> c_out, then the roles alternate
+        ctx.step_pingpong(dv, dyes[s & 1], dyes[(s & 1) ^ 1], drags[s], n, n, synth.DT, synth.DX, ITERS, synth.OMEGA)
 
     for s in range(args.warmup):
         step(s)

@@ -19,6 +19,7 @@ FS_ERR_INVALID_ARG = -1
 FS_ERR_NO_CONTEXT = -2
 FS_ERR_UNSUPPORTED = -3
 FS_ERR_HALO_OVERRUN = -4
+FS_ERR_HALO_TIMEOUT = -5
 
 
 class HaloCopy(C.Structure):
@@ -67,6 +68,7 @@ def lib() -> C.CDLL:
         "fs_apply_drags": ([vp, vp, I, I, I, vp], I),
         "fs_poisson_residual": ([C.POINTER(f), C.POINTER(C.c_double), vp, vp, I, I, f, vp], I),
         "fs_step": ([vp, vp, vp, I, I, I, f, f, I, f, vp, vp, vp], I),
+        "fs_step_pingpong": ([vp, vp, vp, vp, I, I, I, f, f, I, f, vp, vp, vp], I),
         "fs_upscale4_rgb565": ([vp, vp, I, I, vp], I),
         "fs_ensemble_step": ([vp, vp, vp, vp, I, I, I, I, f, f, I, f, I, vp], I),
         "fsh_advect_vec2f": ([vp, vp, vp, I, I, f, I, vp], I),

@@ -30,6 +30,7 @@ struct fs_ctx {
     size_t max_smem_optin;
     unsigned int solve_gen;     // generation stamp of the single-launch solve's completion flags
     int opt_sor_one_launch;
+    int opt_halo_timeout_ms;
     int opt_sor, opt_sor_t, opt_sor_shape, opt_advect, opt_fuse;
 };
 
@@ -255,6 +256,7 @@ const char *fs_error_string(int code)
         case FS_ERR_NO_CONTEXT: return "no context";
         case FS_ERR_UNSUPPORTED: return "unsupported";
         case FS_ERR_HALO_OVERRUN: return "advect backtrace left the local window";
+        case FS_ERR_HALO_TIMEOUT: return "halo exchange: a neighbour never signalled";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
     }
 }
@@ -281,6 +283,7 @@ int fs_ctx_create(fs_ctx **out, int device, void *stream)
     ctx->opt_sor_t = 8;
     ctx->opt_sor_shape = 3;
     ctx->opt_sor_one_launch = 0;
+    ctx->opt_halo_timeout_ms = 10000;
     ctx->opt_advect = 1;
     ctx->opt_fuse = 1;
     cudaError_t e = cudaMalloc(&ctx->status_dev, sizeof(int));
@@ -333,6 +336,7 @@ static int *opt_slot(fs_ctx *ctx, const char *name)
     if (!strcmp(name, "sor_t")) return &ctx->opt_sor_t;
     if (!strcmp(name, "sor_shape")) return &ctx->opt_sor_shape;
     if (!strcmp(name, "sor_one_launch")) return &ctx->opt_sor_one_launch;
+    if (!strcmp(name, "halo_timeout_ms")) return &ctx->opt_halo_timeout_ms;
     if (!strcmp(name, "advect")) return &ctx->opt_advect;
     if (!strcmp(name, "fuse")) return &ctx->opt_fuse;
     return nullptr;
@@ -456,24 +460,40 @@ int fs_apply_drags(fs_vec2f *v, const fs_drag *drags, int n, int dim_x, int dim_
     return launch_apply_drags(mk(ctx), (float2 *)v, drags, n, geo_full(dim_x, dim_y));
 }
 
+int fs_step_pingpong(fs_vec2f *v, const fs_rgb_uq32 *c_in, fs_rgb_uq32 *c_out, const fs_drag *drags,
+                     int n_drags, int dim_x, int dim_y, float dt, float dx, int iters, float omega,
+                     float *p_out, float *div_out, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!v || !c_in || !c_out || c_in == c_out || n_drags < 0 || (n_drags > 0 && !drags) ||
+        bad_dims(dim_x, dim_y) || iters < 0)
+        return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    const size_t n = (size_t)dim_x * dim_y;
+    void *v_tmp, *p = p_out, *d = div_out;
+    int e;
+    if ((e = ensure(ctx, S_VTMP, n * sizeof(fs_vec2f), &v_tmp))) return e;
+    if (!p && (e = ensure(ctx, S_P, n * sizeof(float), &p))) return e;
+    if (!d && (e = ensure(ctx, S_DIV, n * sizeof(float), &d))) return e;
+    return core_step(ctx, v, (fs_vec2f *)v_tmp, c_in, c_out, drags, n_drags, dim_x, dim_y, dt, dx, iters,
+                     omega, (float *)p, (float *)d);
+}
+
 int fs_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags, int n_drags, int dim_x, int dim_y,
             float dt, float dx, int iters, float omega, float *p_out, float *div_out, fs_ctx *ctx)
 {
     if (!ctx) return FS_ERR_NO_CONTEXT;
-    if (!v || !c || n_drags < 0 || (n_drags > 0 && !drags) || bad_dims(dim_x, dim_y) || iters < 0)
-        return FS_ERR_INVALID_ARG;
+    if (!c || bad_dims(dim_x, dim_y)) return FS_ERR_INVALID_ARG;
     DeviceGuard guard(ctx->device);
     const size_t n = (size_t)dim_x * dim_y;
-    void *v_tmp, *c_tmp, *p = p_out, *d = div_out;
+    void *c_tmp;
     int e;
-    if ((e = ensure(ctx, S_VTMP, n * sizeof(fs_vec2f), &v_tmp))) return e;
     if ((e = ensure(ctx, S_CTMP, n * sizeof(fs_rgb_uq32), &c_tmp))) return e;
-    if (!p && (e = ensure(ctx, S_P, n * sizeof(float), &p))) return e;
-    if (!d && (e = ensure(ctx, S_DIV, n * sizeof(float), &d))) return e;
-    if ((e = core_step(ctx, v, (fs_vec2f *)v_tmp, c, (fs_rgb_uq32 *)c_tmp, drags, n_drags, dim_x,
-                       dim_y, dt, dx, iters, omega, (float *)p, (float *)d)))
+    if ((e = fs_step_pingpong(v, c, (fs_rgb_uq32 *)c_tmp, drags, n_drags, dim_x, dim_y, dt, dx, iters, omega,
+                              p_out, div_out, ctx)))
         return e;
-    // the reference swaps pointers (ino:286); a raw-pointer ABI has to copy back
+    // the reference swaps pointers (ino:286); an in-place raw-pointer ABI has to copy back —
+    // fs_step_pingpong is the entry point without this copy
     FS_CUDA_TRY(cudaMemcpyAsync(c, c_tmp, n * sizeof(fs_rgb_uq32), cudaMemcpyDeviceToDevice,
                                 ctx->stream));
     return FS_OK;
@@ -892,9 +912,10 @@ int fs_halo_exchange(const fs_halo_copy *copies, int n_copies, void *const *sign
         a.wait[k] = (unsigned long long *)wait_flags[k];
     }
     a.seq = seq;
+    a.timeout_ns = ctx->opt_halo_timeout_ms > 0 ? (unsigned long long)ctx->opt_halo_timeout_ms * 1000000ull : 0ull;
     a.n_copies = n_copies;
     a.n_peers = n_peers;
-    return launch_halo_exchange(mk(ctx), a, ctx->halo_done_dev);
+    return launch_halo_exchange(mk(ctx), a, ctx->halo_done_dev, ctx->status_dev);
 }
 
 }  // extern "C"

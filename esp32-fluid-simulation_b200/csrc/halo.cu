@@ -20,8 +20,15 @@
 
 namespace fs {
 
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(256)
-halo_exchange_kernel(const HaloArgs a, unsigned int *done_counter)
+halo_exchange_kernel(const HaloArgs a, unsigned int *done_counter, int *status)
 {
     // ---- 1. push ---------------------------------------------------------------------------
     // blocks are dealt to copies in proportion to their size (prefix sums in a.block_end)
@@ -49,14 +56,23 @@ halo_exchange_kernel(const HaloArgs a, unsigned int *done_counter)
     if (threadIdx.x < a.n_peers) {
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.signal[threadIdx.x]), "l"(a.seq) : "memory");
         // ---- 3. wait -----------------------------------------------------------------------------
+        // A neighbour that never signals (a crashed rank) must not hang this GPU: give up after
+        // a.timeout_ns and raise the context's status flag (read by fs_tile_check).
         unsigned long long seen;
-        do {
+        const unsigned long long t0 = global_ns();
+        for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.wait[threadIdx.x]) : "memory");
-        } while (seen < a.seq);
+            if (seen >= a.seq) break;
+            if (a.timeout_ns && global_ns() - t0 > a.timeout_ns) {
+                if (status) atomicExch(status, FS_ERR_HALO_TIMEOUT);
+                break;
+            }
+            __nanosleep(200);
+        }
     }
 }
 
-int launch_halo_exchange(const Launch &L, HaloArgs &a, unsigned int *done_counter)
+int launch_halo_exchange(const Launch &L, HaloArgs &a, unsigned int *done_counter, int *status)
 {
     if (a.n_copies < 0 || a.n_copies > HALO_MAX_COPIES || a.n_peers < 0 || a.n_peers > HALO_MAX_PEERS)
         return (int)cudaErrorInvalidValue;
@@ -77,7 +93,7 @@ int launch_halo_exchange(const Launch &L, HaloArgs &a, unsigned int *done_counte
         a.block_end[c] = blocks;
     }
     if (blocks == 0) blocks = 1;   // nothing to copy: still signal + wait
-    halo_exchange_kernel<<<blocks, 256, 0, L.stream>>>(a, done_counter);
+    halo_exchange_kernel<<<blocks, 256, 0, L.stream>>>(a, done_counter, status);
     ++*L.launches;
     return (int)cudaGetLastError();
 }

@@ -84,9 +84,10 @@ struct HaloArgs {
     unsigned long long *signal[HALO_MAX_PEERS];  // the neighbours' flag slots for this rank
     unsigned long long *wait[HALO_MAX_PEERS];    // this rank's flag slots, one per neighbour
     unsigned long long seq;
+    unsigned long long timeout_ns;               // 0 = wait forever
     int n_copies, n_peers;
 };
-int launch_halo_exchange(const Launch &L, HaloArgs &a, unsigned int *done_counter);
+int launch_halo_exchange(const Launch &L, HaloArgs &a, unsigned int *done_counter, int *status);
 
 // upscale.cu — ino:116-177
 int launch_upscale4_rgb565(const Launch &L, uint16_t *out, const uint32_t *c, int dim_x, int dim_y);

@@ -37,6 +37,19 @@ __device__ __forceinline__ float sor_update_interior(float pc, float l, float r,
     return __fadd_rn(__fmul_rn(k.keep, pc), __fmul_rn(k.omega, gs));
 }
 
+// The same update with the Gauss-Seidel coefficient as an operand.  With every MISSING neighbour
+// passed as +0.0f, ((L + R) + D) + U is bit-identical to pois_gs_safe's running sum (poisson.cpp:
+// 71-86: start from +0, add the existing neighbours in the order L, R, D, U) — adding +0 is exact and
+// neither chain can produce -0 once a +0 took part — and coef = neg_a_ii_inv[#neighbours]
+// (poisson.cpp:67,88) makes it pois_sor_safe; coef = -0.25f makes it pois_sor_fast.
+__device__ __forceinline__ float sor_update_coef(float pc, float l, float r, float d, float u, float dxd,
+                                                 float coef, const SorCoef &k)
+{
+    const float sum = __fadd_rn(__fadd_rn(__fadd_rn(l, r), d), u);
+    const float gs = __fmul_rn(coef, __fsub_rn(dxd, sum));
+    return __fadd_rn(__fmul_rn(k.keep, pc), __fmul_rn(k.omega, gs));
+}
+
 // pois_sor_safe / pois_gs_safe, poisson.cpp:63-99: start from 0, add the
 // EXISTING neighbours in order L, R, D, U, divide by their count via the table.
 __device__ __forceinline__ float sor_update_wall(float pc, float l, float r, float d, float u,

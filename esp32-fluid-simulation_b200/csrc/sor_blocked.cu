@@ -58,68 +58,73 @@ struct BlockedArgs {
     int vec_ok;          // rows are 16-byte aligned: float4 loads/stores allowed
 };
 
-template <bool WALL>
-__device__ __forceinline__ float update_node(float pc, float l, float r, float d, float u, float dxd,
-                                             const SorCoef &k, int gi, int gj, int GX, int GY)
-{
-    if constexpr (!WALL) {
-        return sor_update_interior(pc, l, r, d, u, dxd, k);
-    } else {
-        if ((unsigned)gi >= (unsigned)GX || (unsigned)gj >= (unsigned)GY) return pc;  // not a node
-        const bool hl = gi > 0, hr = gi < GX - 1, hd = gj > 0, hu = gj < GY - 1;
-        if (hl && hr && hd && hu) return sor_update_interior(pc, l, r, d, u, dxd, k);
-        return sor_update_wall(pc, l, r, d, u, hl, hr, hd, hu, dxd, k);
-    }
-}
-
 // One colour over a warp's strip.  Q = colour offset inside the strip: row r
 // updates columns {0,2} when (r+Q) is even and {1,3} when it is odd.
-template <int R, int Q, bool WALL>
+//
+// WALL: 0 = the region lies strictly inside the domain: pois_sor_fast everywhere.
+// Regions that touch a domain wall or stick out of the domain are handled WITHOUT per-node
+// branches: every cell outside the domain holds +0.0f for the whole pass (zero-filled by the
+// loader, never updated), so the interior sum ((L + R) + D) + U of a wall node is bit-identical to
+// pois_gs_safe's sum over its existing neighbours (sor.cuh: sor_update_coef), and the only per-node
+// difference left is the coefficient neg_a_ii_inv[#neighbours]:
+//   1 = only y-walls in reach (CTA-uniform): the coefficient is a row-uniform value, rows outside
+//       the domain are skipped — costs a compare and a branch per row;
+//   2 = x-walls in reach: additionally a per-column select of the coefficient and of "is a node".
+// (The first version branched per node into sor_update_wall: wall tiles cost 3x an interior tile
+// and 24 % of the kernel's instructions.)
+template <int R, int Q, int WALL>
 __device__ __forceinline__ void strip_half_sweep(float (&p)[R][4], const float (&dxd)[R][4],
                                                  const float (&dn)[4], const float (&up)[4],
                                                  const SorCoef &k, int gi0, int gj0, int GX, int GY)
 {
-    // In a region that touches a wall, only the rows at/after a horizontal wall (warp-uniform) and
-    // the lanes whose four columns reach a vertical wall need the per-node wall logic.
-    const bool lane_generic = WALL && (gi0 <= 0 || gi0 + 3 >= GX - 1);
+    bool node[4], wallc[4];
+    if constexpr (WALL == 2) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            node[c] = (unsigned)(gi0 + c) < (unsigned)GX;
+            wallc[c] = gi0 + c == 0 || gi0 + c == GX - 1;
+        }
+    }
+    auto upd = [&](int r, int c, float l, float rr, float d, float u, float c_in, float c_wall) {
+        if constexpr (WALL == 2) {
+            const float n = sor_update_coef(p[r][c], l, rr, d, u, dxd[r][c], wallc[c] ? c_wall : c_in, k);
+            p[r][c] = node[c] ? n : p[r][c];
+        } else if constexpr (WALL == 1) {
+            p[r][c] = sor_update_coef(p[r][c], l, rr, d, u, dxd[r][c], c_in, k);
+        } else {
+            p[r][c] = sor_update_interior(p[r][c], l, rr, d, u, dxd[r][c], k);
+        }
+    };
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int gj = gj0 + r;
-        const bool generic = WALL && (lane_generic || gj <= 0 || gj >= GY - 1);
+        float c_in = k.neg_quarter, c_wall = k.neg_third;
+        if constexpr (WALL != 0) {
+            if ((unsigned)gj >= (unsigned)GY) continue;          // not a row of the domain (warp-uniform)
+            const bool wallr = gj == 0 || gj == GY - 1;
+            c_in = wallr ? k.neg_third : k.neg_quarter;          // 3 or 4 neighbours
+            c_wall = wallr ? k.neg_half : k.neg_third;           // 2 (corner) or 3
+        }
         if (((r + Q) & 1) == 0) {
             const float lft = __shfl_up_sync(0xffffffffu, p[r][3], 1);
             const float d0 = r > 0 ? p[r > 0 ? r - 1 : 0][0] : dn[0], u0 = r < R - 1 ? p[r < R - 1 ? r + 1 : 0][0] : up[0];
             const float d2 = r > 0 ? p[r > 0 ? r - 1 : 0][2] : dn[2], u2 = r < R - 1 ? p[r < R - 1 ? r + 1 : 0][2] : up[2];
-            float n0, n2;
-            if (generic) {
-                n0 = update_node<true>(p[r][0], lft, p[r][1], d0, u0, dxd[r][0], k, gi0 + 0, gj, GX, GY);
-                n2 = update_node<true>(p[r][2], p[r][1], p[r][3], d2, u2, dxd[r][2], k, gi0 + 2, gj, GX, GY);
-            } else {
-                n0 = sor_update_interior(p[r][0], lft, p[r][1], d0, u0, dxd[r][0], k);
-                n2 = sor_update_interior(p[r][2], p[r][1], p[r][3], d2, u2, dxd[r][2], k);
-            }
-            p[r][0] = n0;
-            p[r][2] = n2;
+            const float c1 = p[r][1], c3 = p[r][3];
+            upd(r, 0, lft, c1, d0, u0, c_in, c_wall);
+            upd(r, 2, c1, c3, d2, u2, c_in, c_wall);
         } else {
             const float rgt = __shfl_down_sync(0xffffffffu, p[r][0], 1);
             const float d1 = r > 0 ? p[r > 0 ? r - 1 : 0][1] : dn[1], u1 = r < R - 1 ? p[r < R - 1 ? r + 1 : 0][1] : up[1];
             const float d3 = r > 0 ? p[r > 0 ? r - 1 : 0][3] : dn[3], u3 = r < R - 1 ? p[r < R - 1 ? r + 1 : 0][3] : up[3];
-            float n1, n3;
-            if (generic) {
-                n1 = update_node<true>(p[r][1], p[r][0], p[r][2], d1, u1, dxd[r][1], k, gi0 + 1, gj, GX, GY);
-                n3 = update_node<true>(p[r][3], p[r][2], rgt, d3, u3, dxd[r][3], k, gi0 + 3, gj, GX, GY);
-            } else {
-                n1 = sor_update_interior(p[r][1], p[r][0], p[r][2], d1, u1, dxd[r][1], k);
-                n3 = sor_update_interior(p[r][3], p[r][2], rgt, d3, u3, dxd[r][3], k);
-            }
-            p[r][1] = n1;
-            p[r][3] = n3;
+            const float c0 = p[r][0], c2 = p[r][2];
+            upd(r, 1, c0, c2, d1, u1, c_in, c_wall);
+            upd(r, 3, c2, rgt, d3, u3, c_in, c_wall);
         }
     }
 }
 
 // all H half-sweeps of one pass over a warp's strip, with the inter-warp row mailbox
-template <int R, int NW, bool WALL>
+template <int R, int NW, int WALL>
 __device__ __forceinline__ void sweep_pass(float (&p)[R][4], const float (&dxd)[R][4], const BlockedArgs &a,
                                            float4 (*mail)[NW][2][32], int gi0, int gj0, int n_half)
 {
@@ -188,12 +193,25 @@ __device__ __forceinline__ void rowmajor_coords(int idx, int ntx, int &tx, int &
     tx = idx - ty * ntx;
 }
 
-// does a region touch a domain wall or stick out of the domain?  (CTA-uniform)
+// does a region touch a domain wall or stick out of the domain?  (CTA-uniform)  0 = no,
+// 1 = y-walls only, 2 = x-walls (and possibly y-walls): the WALL mode of strip_half_sweep
 template <int R, int NW>
-__device__ __forceinline__ bool region_hits_wall(const BlockedArgs &a, int rlx0, int rly0)
+__device__ __forceinline__ int region_wall_mode(const BlockedArgs &a, int rlx0, int rly0)
 {
     const int rgx0 = a.g.ox + rlx0, rgy0 = a.g.oy + rly0;
-    return rgx0 <= 0 || rgy0 <= 0 || rgx0 + BLK_RW >= a.g.GX || rgy0 + R * NW >= a.g.GY;
+    if (rgx0 <= 0 || rgx0 + BLK_RW >= a.g.GX) return 2;
+    return (rgy0 <= 0 || rgy0 + R * NW >= a.g.GY) ? 1 : 0;
+}
+
+template <int R, int NW>
+__device__ __forceinline__ void sweep_region(float (&p)[R][4], const float (&dxd)[R][4], const BlockedArgs &a,
+                                             float4 (*mail)[NW][2][32], int rlx0, int rly0, int gi0, int gj0,
+                                             int n_half)
+{
+    const int mode = region_wall_mode<R, NW>(a, rlx0, rly0);
+    if (mode == 0)      sweep_pass<R, NW, 0>(p, dxd, a, mail, gi0, gj0, n_half);
+    else if (mode == 1) sweep_pass<R, NW, 1>(p, dxd, a, mail, gi0, gj0, n_half);
+    else                sweep_pass<R, NW, 2>(p, dxd, a, mail, gi0, gj0, n_half);
 }
 
 // ---- loader 1: one tile per CTA, region read straight from global into registers ---------------
@@ -237,8 +255,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) sor_blocked_kernel(const Blocke
             }
         }
     }
-    if (!region_hits_wall<R, NW>(a, rlx0, rly0)) sweep_pass<R, NW, false>(p, dxd, a, mail, gi0, gj0, a.n_half);
-    else                                          sweep_pass<R, NW, true>(p, dxd, a, mail, gi0, gj0, a.n_half);
+    sweep_region<R, NW>(p, dxd, a, mail, rlx0, rly0, gi0, gj0, a.n_half);
     store_tile<R>(p, a, a.p_out, rlx0, rly0, lx0, ly0);
 }
 
@@ -326,8 +343,7 @@ sor_blocked_tma_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_c
             prefetch(ahead);
             ahead = atomicAdd(work_counter, 1);   // consumed one tile later
         }
-        if (!region_hits_wall<R, NW>(a, rlx0, rly0)) sweep_pass<R, NW, false>(p, dxd, a, mail, gi0, gj0, a.n_half);
-        else                                          sweep_pass<R, NW, true>(p, dxd, a, mail, gi0, gj0, a.n_half);
+        sweep_region<R, NW>(p, dxd, a, mail, rlx0, rly0, gi0, gj0, a.n_half);
         store_tile<R>(p, a, a.p_out, rlx0, rly0, lx0, ly0);
     }
 }
@@ -461,8 +477,7 @@ sor_solve_tma_kernel(const __grid_constant__ CUtensorMap d_map, const __grid_con
             }
         }
         const int n_half = k == sa.passes - 1 ? sa.n_half_last : a.n_half;
-        if (!region_hits_wall<R, NW>(a, rlx0, rly0)) sweep_pass<R, NW, false>(p, dxd, a, mail, gi0, gj0, n_half);
-        else                                          sweep_pass<R, NW, true>(p, dxd, a, mail, gi0, gj0, n_half);
+        sweep_region<R, NW>(p, dxd, a, mail, rlx0, rly0, gi0, gj0, n_half);
         store_tile<R>(p, a, sa.buf[k & 1], rlx0, rly0, lx0, ly0);
         __syncthreads();                       // the whole tile has been stored
         if (threadIdx.x == 0) {

@@ -202,6 +202,20 @@ class Context:
         check(fn(a_v, a_c, d.ctypes.data if nd else None, nd, dim_x, dim_y, dt, dx, iters, omega,
                  a_p or None, a_d or None, self._h), "step")
 
+    def step_pingpong(self, v, c_in, c_out, drags, dim_x, dim_y, dt, dx, iters, omega, p_out=None, div_out=None):
+        """loop() body with the dye going c_in -> c_out (the caller swaps, ino:286); device tensors."""
+        n = dim_x * dim_y
+        a_v, d0 = _ptr(v, "float32", 2 * n)
+        a_ci, d1 = _ptr(c_in, "uint32", 3 * n)
+        a_co, d2 = _ptr(c_out, "uint32", 3 * n)
+        a_p, _ = _ptr(p_out, "float32", n)
+        a_d, _ = _ptr(div_out, "float32", n)
+        if not (d0 and d1 and d2):
+            raise ValueError("step_pingpong: device tensors only")
+        d, nd = _drags(drags)
+        check(self._L.fs_step_pingpong(a_v, a_ci, a_co, d.ctypes.data if nd else None, nd, dim_x, dim_y, dt, dx,
+                                       iters, omega, a_p or None, a_d or None, self._h), "fs_step_pingpong")
+
     def upscale4_rgb565(self, out, c, dim_x, dim_y):
         a_o, d0 = _ptr(out, "uint16", 16 * (dim_x - 1) * (dim_y - 1))
         a_c, d1 = _ptr(c, "uint32", 3 * dim_x * dim_y)

@@ -43,6 +43,7 @@ extern "C" {
 #define FS_ERR_NO_CONTEXT (-2)
 #define FS_ERR_UNSUPPORTED (-3)
 #define FS_ERR_HALO_OVERRUN (-4)  /* decomposed advect: backtrace left the local window */
+#define FS_ERR_HALO_TIMEOUT (-5)  /* fs_halo_exchange: a neighbour never signalled (see "halo_timeout_ms") */
 /* positive values are cudaError_t codes */
 
 typedef struct fs_vec2f { float x, y; } fs_vec2f;             /* Vector2<float>, vector.h:4-57 */
@@ -71,6 +72,8 @@ int  fs_ctx_synchronize(fs_ctx *ctx);
  *              dependencies between passes (shapes 2, 3, 5); 0 (default) = one launch per pass.
  *              Measured: the dependency probes and release fences on the issuing thread cost more
  *              than the launch gaps and per-pass tails they remove (0.98 vs 0.87 ms at 4096^2)
+ *   "halo_timeout_ms": how long fs_halo_exchange waits for a neighbour's flag before raising
+ *              FS_ERR_HALO_TIMEOUT in the context's status (reported by fs_tile_check); default 10000, 0 = forever
  *   "advect" : 0 = direct L1/L2 gather, 1 = TMA-staged shared-memory tile (default where legal)
  *   "fuse"   : bit mask for fs_step: 1 = drags + divergence folded into the velocity advect, 2 =
  *              gradient-subtract folded into the dye advect (measured slower than the stand-alone
@@ -122,6 +125,13 @@ int fs_apply_drags(fs_vec2f *v, const fs_drag *drags, int n, int dim_x, int dim_
 int fs_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags, int n_drags,
             int dim_x, int dim_y, float dt, float dx, int iters, float omega,
             float *p_out, float *div_out, fs_ctx *ctx);
+/* The same loop() body with the reference's dye pointer swap (ino:281-287) left to the caller:
+ * the dye is read from c_in and the advected dye written to c_out (distinct buffers; the caller
+ * alternates them from step to step like SWAP(c_temp, color_field)).  Saves fs_step's copy-back
+ * of the dye (12 B/node read + written). */
+int fs_step_pingpong(fs_vec2f *v, const fs_rgb_uq32 *c_in, fs_rgb_uq32 *c_out, const fs_drag *drags,
+                     int n_drags, int dim_x, int dim_y, float dt, float dx, int iters, float omega,
+                     float *p_out, float *div_out, fs_ctx *ctx);
 /* draw_routine arithmetic, ino:116-177: 4x bilinear upscale of the dye, UQ32
  * round, RGB565 pack, byte swap.  out is (dim_x-1)*4 rows x (dim_y-1)*4 columns
  * of uint16, row pitch (dim_y-1)*4 (image rows run along the sim's fast axis). */

@@ -268,11 +268,86 @@ class Ref(_Base):
         L.ref_fill_rand.argtypes = [F, U, I, I, C.c_uint]
         L.ref_fill_rand.restype = None
 
+        # the sketch itself (ESP32-fluid-simulation.ino, compiled unmodified by ino_shim.cpp)
+        self.has_ino = hasattr(L, "ref_ino_loop")
+        if self.has_ino:
+            L.ref_ino_setup.argtypes = [F, U, I, I]
+            L.ref_ino_loop.argtypes = [F, U, C.c_void_p, I, I, I]
+            L.ref_ino_draw.argtypes = [C.POINTER(C.c_uint16), U, I, I]
+            L.ref_ino_touch.argtypes = [C.c_void_p, I, C.POINTER(C.c_int), I]
+            L.ref_ino_touch.restype = I
+            for n in ("ref_ino_setup", "ref_ino_loop", "ref_ino_draw"):
+                getattr(L, n).restype = None
+
     def saturates(self) -> bool:
         return bool(self.lib.ref_saturates())
+
+    # --- the sketch's own routines -------------------------------------------------------------
+    def ino_setup(self, dim_x, dim_y):
+        """setup(), ino:194-246: (velocity, dye) initial condition."""
+        v = np.empty((dim_y, dim_x, 2), np.float32)
+        c = np.empty((dim_y, dim_x, 3), np.uint32)
+        self.lib.ref_ino_setup(_f32(v), _u32(c), dim_x, dim_y)
+        return v, c
+
+    def ino_loop(self, v, c, drags=None):
+        """loop(), ino:249-289, in place (K=10, omega=1.96, dt=1/30 are the sketch's literals)."""
+        dx_, dy_ = _dims(v)
+        drags = np.ascontiguousarray(drags if drags is not None else np.zeros(0, DRAG_DTYPE), DRAG_DTYPE)
+        assert all(int(d["cy"]) < dx_ and int(d["cx"]) < dy_ for d in drags), "ino:266-268 writes out of bounds"
+        self.lib.ref_ino_loop(_f32(v), _u32(c), drags.ctypes.data, len(drags), dx_, dy_)
+        return v, c
+
+    def ino_draw(self, c):
+        """draw_routine(), ino:99-191: the RGB565 frame, (dim_x-1)*4 rows x (dim_y-1)*4 columns."""
+        dx_, dy_ = _dims(c)
+        out = np.empty(((dx_ - 1) * 4, (dy_ - 1) * 4), np.uint16)
+        self.lib.ref_ino_draw(out.ctypes.data_as(C.POINTER(C.c_uint16)), _u32(c), dx_, dy_)
+        return out
+
+    def ino_touch(self, samples):
+        """touch_routine(), ino:63-96: samples = [(touched, raw_x, raw_y)] per 10 ms poll -> drag records
+        (at most 10: the queue depth)."""
+        s = np.ascontiguousarray(samples, np.int32).reshape(-1, 3)
+        out = np.zeros(16, DRAG_DTYPE)
+        n = self.lib.ref_ino_touch(out.ctypes.data, len(out), s.ctypes.data_as(C.POINTER(C.c_int)), len(s))
+        return out[:n].copy()
 
     def fill_rand(self, dim_x, dim_y, seed=1):
         v = np.empty((dim_y, dim_x, 2), np.float32)
         c = np.empty((dim_y, dim_x, 3), np.uint32)
         self.lib.ref_fill_rand(_f32(v), _u32(c), dim_x, dim_y, seed)
         return v, c
+
+
+class Checker(Oracle):
+    """What the parity tests compare against: the reference's OWN compiled code (oracle/_ref) for
+    every operator it exports — advect, divergence, gradient, poisson_solve, drags, the loop() order
+    — whenever that library is present and this host saturates float->uint32 like CUDA; the
+    plain-C port (pinned against it in tests/test_oracle_vs_ref.py) for the window operators and
+    wherever oracle/_ref is unavailable.  ``kind`` says which one answered."""
+
+    def __init__(self):
+        super().__init__()
+        self.kind = "port"
+        self.ref = None
+        if have_ref():
+            try:
+                r = Ref()
+            except OSError:
+                r = None
+            if r is not None and r.saturates():
+                self.ref = r
+                self._fn.update(r._fn)     # same signatures, ref_* instead of oracle_*
+                self.kind = "reference"
+
+    # ino:116-177 and ino:196-241 from the compiled sketch where available
+    def upscale4_rgb565(self, c):
+        if self.ref is not None and self.ref.has_ino:
+            return self.ref.ino_draw(c)
+        return super().upscale4_rgb565(c)
+
+    def init_color_wheel(self, dim_x, dim_y):
+        if self.ref is not None and self.ref.has_ino:
+            return self.ref.ino_setup(dim_x, dim_y)
+        return super().init_color_wheel(dim_x, dim_y)

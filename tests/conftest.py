@@ -40,6 +40,16 @@ def built():
 
 @pytest.fixture(scope="session")
 def oracle(built):
+    """The checker: the reference's own compiled code where oracle/_ref is present (it ships to
+    the GPU box), the pinned C port otherwise / for the window operators."""
+    from oracle import Checker
+    chk = Checker()
+    print(f"[conftest] parity checker = {chk.kind}")
+    return chk
+
+
+@pytest.fixture(scope="session")
+def port(built):
     from oracle import Oracle
     return Oracle()
 

@@ -118,6 +118,31 @@ def test_poisson_solve_every_blocking_depth(ctx, oracle, t_block, shape, one_lau
         ctx.set_option("sor_one_launch", 0)
 
 
+@pytest.mark.parametrize("shape", [(2, 2), (4, 3), (61, 81), (128, 192), (129, 193), (260, 200), (1023, 517), (1024, 520)])
+@pytest.mark.parametrize("field", ["signed-zeros", "sparse", "denormal"])
+def test_poisson_walls_and_zeros(ctx, oracle, shape, field):
+    """The blocked kernel treats walls without branches: cells outside the domain hold +0 and the
+    interior sum is used for wall nodes (poisson.cpp:63-99 vs :101-112).  That is bit-identical only if
+    signs of zero and tiny values behave exactly like the reference's running sum — probe exactly those."""
+    dim_x, dim_y = shape
+    rng = np.random.default_rng(dim_x * 1000 + dim_y)
+    d = rng.normal(0, 20, (dim_y, dim_x)).astype(np.float32)
+    if field == "signed-zeros":
+        d[rng.random(d.shape) < 0.5] = 0.0
+        d[rng.random(d.shape) < 0.3] = -0.0
+    elif field == "sparse":
+        d[:] = 0.0
+        d[dim_y // 2, dim_x // 2] = -3.0
+        d[0, 0] = 1.0
+        d[-1, -1] = -0.0
+    else:
+        d = (d * np.float32(1e-41)).astype(np.float32)     # denormal divergence -> denormal pressures
+    for iters, omega in ((9, 1.96), (3, 1.0), (17, 0.7)):
+        p = torch.full((dim_y, dim_x), -7.0, dtype=torch.float32, device="cuda")
+        ctx.poisson_solve(p, to_dev(d), dim_x, dim_y, 1.0, iters, omega)
+        assert_bit_equal(to_host(p), oracle.poisson_solve(d, 1.0, iters, omega), f"{field} K={iters} w={omega}")
+
+
 def test_half_sweep_colours(ctx, oracle):
     dim_x, dim_y = 61, 81
     rng = np.random.default_rng(8)
@@ -190,6 +215,25 @@ def test_step_matches_oracle(ctx, oracle, shape, iters, steps, fuse):
             assert_bit_equal(g, w, f"{name} after {steps} steps")
     finally:
         ctx.set_option("fuse", 1)
+
+
+def test_step_pingpong_equals_step(ctx, oracle):
+    """fs_step_pingpong (dye c_in -> c_out, the caller swaps like ino:286) == fs_step == the reference."""
+    from esp32_fluid_simulation_b200 import synth
+    dim_x, dim_y, iters, steps = 320, 200, 20, 4
+    v, c = synth.velocity(dim_x, dim_y, vmax=80.0), synth.dye(dim_x, dim_y)
+    drs = [synth.drags(dim_x, dim_y, s, n=12) for s in range(steps)]
+    dv, ca, cb = to_dev(v), to_dev(c), torch.empty(dim_y, dim_x, 3, dtype=torch.int32, device="cuda")
+    for dr in drs:
+        ctx.step_pingpong(dv, ca, cb, dr, dim_x, dim_y, DT, 1.0, iters, 1.96)
+        ca, cb = cb, ca
+    ov, oc = v.copy(), c.copy()
+    for dr in drs:
+        ov, oc = oracle.step(ov, oc, dr, DT, 1.0, iters, 1.96)
+    assert_bit_equal(to_host(dv), ov, "v")
+    assert_bit_equal(to_host(ca, np.uint32), oc, "c")
+    with pytest.raises(Exception):
+        ctx.step_pingpong(dv, ca, ca, None, dim_x, dim_y, DT, 1.0, iters, 1.96)   # c_in must differ from c_out
 
 
 def test_step_golden_regression(ctx, golden):
