@@ -274,7 +274,7 @@ class Ref(_Base):
             L.ref_ino_setup.argtypes = [F, U, I, I]
             L.ref_ino_loop.argtypes = [F, U, C.c_void_p, I, I, I]
             L.ref_ino_draw.argtypes = [C.POINTER(C.c_uint16), U, I, I]
-            L.ref_ino_touch.argtypes = [C.c_void_p, I, C.POINTER(C.c_int), I]
+            L.ref_ino_touch.argtypes = [C.c_void_p, I, C.POINTER(C.c_int), I, I, I]
             L.ref_ino_touch.restype = I
             for n in ("ref_ino_setup", "ref_ino_loop", "ref_ino_draw"):
                 getattr(L, n).restype = None
@@ -305,12 +305,13 @@ class Ref(_Base):
         self.lib.ref_ino_draw(out.ctypes.data_as(C.POINTER(C.c_uint16)), _u32(c), dx_, dy_)
         return out
 
-    def ino_touch(self, samples):
+    def ino_touch(self, samples, dim_x=61, dim_y=81):
         """touch_routine(), ino:63-96: samples = [(touched, raw_x, raw_y)] per 10 ms poll -> drag records
         (at most 10: the queue depth)."""
         s = np.ascontiguousarray(samples, np.int32).reshape(-1, 3)
         out = np.zeros(16, DRAG_DTYPE)
-        n = self.lib.ref_ino_touch(out.ctypes.data, len(out), s.ctypes.data_as(C.POINTER(C.c_int)), len(s))
+        n = self.lib.ref_ino_touch(out.ctypes.data, len(out), s.ctypes.data_as(C.POINTER(C.c_int)), len(s),
+                                   dim_x, dim_y)
         return out[:n].copy()
 
     def fill_rand(self, dim_x, dim_y, seed=1):

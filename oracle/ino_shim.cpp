@@ -83,8 +83,9 @@ void ref_ino_draw(uint16_t *out, const uint32_t *c, int dim_x, int dim_y)
 
 // touch_routine(), ino:63-96: `n` polls of the panel, samples = {touched, raw x, raw y}.  Returns
 // the number of drag records the task queued (at most the queue depth, 10: ino:49,85), copied to out.
-int ref_ino_touch(void *out, int max_out, const int *samples, int n)
+int ref_ino_touch(void *out, int max_out, const int *samples, int n, int dim_x, int dim_y)
 {
+    set_dims(dim_x, dim_y);                       // map() targets [0, N_COLS] x [0, N_ROWS] (ino:77-78)
     g_touch_script.clear();
     for (int k = 0; k < n; k++) g_touch_script.push_back(TouchSample{samples[3 * k], samples[3 * k + 1], samples[3 * k + 2]});
     g_touch_pos = 0;

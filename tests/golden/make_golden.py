@@ -95,6 +95,29 @@ def main():
     fl = np.array([r.uq32_to_float(int(x)) for x in raws], np.float32)
     np.savez_compressed(os.path.join(HERE, "sample_edges.npz"), v=v, c=c, pts=pts, sv=sv, sc=sc,
                         uq_in=xs, uq_out=uq, raw_in=raws, raw_out=fl)
+    # (5) the SKETCH ITSELF (ESP32-fluid-simulation.ino compiled unmodified by oracle/ino_shim.cpp):
+    # setup() initial condition, draw_routine() frames, touch_routine() drag records, loop() steps
+    ino = {}
+    for dim_x, dim_y in [(61, 81), (5, 4), (16, 9)]:
+        _, c = r.ino_setup(dim_x, dim_y)
+        ino[f"wheel_{dim_x}x{dim_y}"] = c
+    for dim_x, dim_y in [(2, 2), (5, 4), (33, 17), (61, 81)]:
+        _, c = rand_inputs(rng, dim_x, dim_y, 1.0)
+        c[0, 0] = 0xFFFFFFFF                                    # saturating corner
+        ino[f"frame_{dim_x}x{dim_y}_c"] = c
+        ino[f"frame_{dim_x}x{dim_y}"] = r.ino_draw(c)
+    script = [(1, 1950, 2020), (1, 1993, 2020), (0, 0, 0), (1, 500, 500), (1, 500, 559), (1, 3700, 3800),
+              (1, 100, 100), (1, 230, 260), (0, 9, 9), (0, 9, 9), (1, 2000, 2000)]
+    script += [(1, int(x), int(y)) for x, y in rng.integers(150, 3900, (14, 2))]   # > 10 records: the queue drops
+    ino["touch_script"] = np.array(script, np.int32)
+    ino["touch_drags"] = r.ino_touch(script)
+    v, c = rand_inputs(rng, 61, 81, 90.0)
+    dr = rand_drags(rng, 61, 81, 7)
+    ino["loop_v0"], ino["loop_c0"], ino["loop_drags"] = v.copy(), c.copy(), dr
+    for _ in range(3):
+        r.ino_loop(v, c, dr)
+    ino["loop_v"], ino["loop_c"] = v, c
+    np.savez_compressed(os.path.join(HERE, "ino_sketch.npz"), **ino)
     print("golden fixtures written to", HERE)
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

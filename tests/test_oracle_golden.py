@@ -205,3 +205,36 @@ def test_upscale_oracle_matches_independent_numpy_restatement(port, shape):
     c = rng.integers(0, 2 ** 32, (dim_y, dim_x, 3), dtype=np.uint32)
     c[0, 0] = 0xFFFFFFFF                                       # saturating corner
     assert np.array_equal(port.upscale4_rgb565(c), _upscale_numpy(c))
+
+
+# ---- fixtures generated from the compiled sketch (ESP32-fluid-simulation.ino, oracle/ino_shim.cpp) ------
+
+def test_sketch_fixtures_initial_condition(port, golden):
+    from esp32_fluid_simulation_b200 import synth
+    g = golden("ino_sketch.npz")
+    for key in [k for k in g.files if k.startswith("wheel_")]:
+        dim_x, dim_y = (int(t) for t in key[6:].split("x"))
+        assert_bit_equal(port.init_color_wheel(dim_x, dim_y)[1], g[key], f"port {key}")
+        assert_bit_equal(synth.color_wheel(dim_x, dim_y)[1], g[key], f"synth {key}")
+
+
+def test_sketch_fixtures_frames(port, golden):
+    g = golden("ino_sketch.npz")
+    keys = [k for k in g.files if k.startswith("frame_") and k.endswith("_c")]
+    assert len(keys) == 4
+    for key in keys:
+        assert_bit_equal(port.upscale4_rgb565(g[key]), g[key[:-2]], key[:-2])
+
+
+def test_sketch_fixtures_touch_and_loop(port, golden):
+    from esp32_fluid_simulation_b200 import synth
+    g = golden("ino_sketch.npz")
+    want = g["touch_drags"]
+    got = synth.touch_drags([tuple(r) for r in g["touch_script"]], 61, 81)
+    assert len(want) == 10 and len(got) > 10                        # the sketch's queue holds 10 (ino:49)
+    assert_bit_equal(got[:10].view(np.uint8), want.view(np.uint8), "drag records")
+    v, c = g["loop_v0"].copy(), g["loop_c0"].copy()
+    for _ in range(3):
+        port.step(v, c, g["loop_drags"], DT, 1.0, 10, 1.96)
+    assert_bit_equal(v, g["loop_v"], "velocity after 3 loop()s")
+    assert_bit_equal(c, g["loop_c"], "dye after 3 loop()s")
