@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-METRIC = "Mcell-steps/s (advect+project, 50 SOR iters) at 4096^2"
+METRIC = "Mcell-steps/s (advect+project, 50 SOR iters) at 4096^2"   # N>1: 4096^2 nodes PER GPU (config.grid)
 UNIT = "Mcell-steps/s"
 GRID = 4096          # per-GPU tile edge
 ITERS = 50
@@ -181,6 +181,90 @@ def start_watchdog(seconds: float):
     return t
 
 
+def verify_decomposed(fb, torch, dist, local_rank, world, rank, gx, gy, iters, ghost, halo, n_drags) -> dict:
+    """UNTIMED parity leg of bench.py's N>1 arm (runs before the timed region):
+      oracle_small      a 1024x768, K=20, 3-step decomposed run (same code path, same process grid),
+                        gathered on rank 0 and bit-compared with the CPU checker (the reference's own
+                        compiled code when oracle/_ref travelled, else the pinned port);
+      one_gpu_equals_n  one step of THE BENCH GRID: every rank also steps the whole global grid on
+                        its own GPU through fs_step and compares its rectangle bit for bit (the
+                        single-GPU path is oracle-checked at 4096^2 by tests/test_gpu_parity.py)."""
+    from esp32_fluid_simulation_b200 import synth
+    from esp32_fluid_simulation_b200.dist import NativeDist, _device_view
+    dev = torch.device("cuda", local_rank)
+    out = {}
+
+    def connect(sim):
+        handles = [None] * world
+        dist.all_gather_object(handles, sim.ipc_handle())
+        sim.connect(handles)
+
+    # (a) small run against the CPU checker
+    sx, sy, sk, steps = 1024, 768, 20, 3
+    ctx = fb.Context(local_rank, torch.cuda.current_stream(dev))
+    sim = NativeDist(ctx, sx, sy, world, rank, sk, ghost=32, advect_halo=12, dt=synth.DT, dx=synth.DX, omega=synth.OMEGA)
+    connect(sim)
+    w = sim.window
+    sim.upload(synth.velocity(sx, sy, vmax=150.0, window=(w.ox, w.oy, w.nx, w.ny)),
+               synth.dye(sx, sy, window=(w.ox, w.oy, w.nx, w.ny)))
+    drs = [synth.drags(sx, sy, s, n=8, vmax=300.0) for s in range(steps)]
+    for s in range(steps):
+        sim.step(drs[s])
+    sim.check()
+    got = sim.download("vcp")
+    parts = [None] * world
+    dist.all_gather_object(parts, (w.ox + w.x0, w.oy + w.y0, got["v"], got["c"], got["p"]))
+    ok = 1
+    if rank == 0:
+        import oracle as _oracle            # test infrastructure: the checker, never the thing measured
+        _oracle.build()
+        chk = _oracle.Checker()
+        ov, oc = synth.velocity(sx, sy, vmax=150.0), synth.dye(sx, sy)
+        for s in range(steps):
+            ov, oc, op, _ = chk.step(ov, oc, drs[s], synth.DT, synth.DX, sk, synth.OMEGA, want_fields=True)
+        for x0, y0, pv, pc, pp in parts:
+            h, wd = pv.shape[:2]
+            same = (np.array_equal(pv.view(np.uint32), ov[y0:y0 + h, x0:x0 + wd].view(np.uint32)) and
+                    np.array_equal(pc, oc[y0:y0 + h, x0:x0 + wd]) and
+                    np.array_equal(pp.view(np.uint32), op[y0:y0 + h, x0:x0 + wd].view(np.uint32)))
+            ok &= int(same)
+        out["checker"] = chk.kind
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.broadcast(flag, 0)
+    out["oracle_small"] = bool(flag.item())
+    sim.close()
+
+    # (b) the bench grid itself: decomposed step == single-GPU step of the whole grid
+    g = torch.Generator(device=dev).manual_seed(4321)          # same seed, same generator: same field everywhere
+    v = (torch.rand(gy, gx, 2, device=dev, generator=g) - 0.5) * 120.0
+    c = torch.randint(0, 2 ** 31 - 1, (gy, gx, 3), device=dev, dtype=torch.int32, generator=g)
+    sim = NativeDist(ctx, gx, gy, world, rank, iters, ghost=ghost, advect_halo=halo, dt=synth.DT, dx=synth.DX,
+                     omega=synth.OMEGA)
+    connect(sim)
+    w = sim.window
+    sim.upload(v[w.oy:w.oy + w.ny, w.ox:w.ox + w.nx].contiguous(), c[w.oy:w.oy + w.ny, w.ox:w.ox + w.nx].contiguous())
+    dr = synth.drags(gx, gy, 0, n=n_drags)
+    sim.step(dr)
+    sim.check()
+    c2 = torch.empty_like(c)
+    ctx.step_pingpong(v, c, c2, dr, gx, gy, synth.DT, synth.DX, iters, synth.OMEGA)
+    ctx.synchronize()
+    pv, pc, _, _ = sim.device_fields()
+    dv = torch.as_tensor(_device_view(pv, (w.ny, w.nx, 2), "<f4"), device=dev)
+    dc = torch.as_tensor(_device_view(pc, (w.ny, w.nx, 3), "<i4"), device=dev)
+    ys, xs = slice(w.oy + w.y0, w.oy + w.y1), slice(w.ox + w.x0, w.ox + w.x1)
+    same = (torch.equal(dv[w.y0:w.y1, w.x0:w.x1].view(torch.int32), v[ys, xs].view(torch.int32)) and
+            torch.equal(dc[w.y0:w.y1, w.x0:w.x1], c2[ys, xs]))
+    flag = torch.tensor([int(same)], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["one_gpu_equals_n"] = bool(flag.item())
+    out["one_gpu_equals_n_grid"] = [gx, gy]
+    sim.close()
+    del v, c, c2
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -201,6 +285,7 @@ def run_b200_arm(args):
     if world > 1:
         from esp32_fluid_simulation_b200 import dist as fdist
         args.clock_sampler = ClockSampler
+        args.verify_fn = verify_decomposed
         watchdog = start_watchdog(float(os.environ.get("FS_BENCH_WATCHDOG_S", "900")))
         result = fdist.bench_decomposed(args, GRID, args.iters, N_DRAGS)
     else:
@@ -348,6 +433,8 @@ def main():
                     "(BASELINE.json configs[3] = 16384x16384, configs[4] = 24576x32768)")
     ap.add_argument("--iters", type=int, default=ITERS, help="SOR iterations per step (N>1 extra configs)")
     ap.add_argument("--upscale", action="store_true", help="N>1: also produce the 4x RGB565 frame every step")
+    ap.add_argument("--no-verify", action="store_true", help="N>1: skip the untimed parity leg (oracle_small, "
+                    "one_gpu_equals_n) that runs before the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

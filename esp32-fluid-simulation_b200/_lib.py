@@ -34,6 +34,19 @@ class Tile(C.Structure):
                 ("gdim_x", "gdim_y", "ox", "oy", "nx", "ny", "x0", "y0", "x1", "y1")]
 
 
+class DistConfig(C.Structure):
+    """fs_dist_config"""
+    _fields_ = [(n, C.c_int) for n in ("gdim_x", "gdim_y", "world", "rank", "px", "py", "ghost", "advect_halo",
+                                      "iters")] + [(n, C.c_float) for n in ("dt", "dx", "omega")]
+
+
+class DistInfo(C.Structure):
+    """fs_dist_info_t"""
+    _fields_ = [(n, C.c_int) for n in ("px", "py", "n_neighbours", "sor_passes", "sor_t", "div_ring",
+                                      "velocity_halo", "dye_halo", "exchanges_per_step")] + \
+               [("exchanges", C.c_ulonglong), ("arena_bytes", C.c_size_t)]
+
+
 _lib = None
 
 
@@ -93,6 +106,18 @@ def lib() -> C.CDLL:
         "fs_ipc_close": ([vp, vp], I),
         "fs_halo_exchange": ([C.POINTER(HaloCopy), I, C.POINTER(vp), C.POINTER(vp), I, C.c_ulonglong, vp], I),
         "fs_ctx_set_stream": ([vp, vp], I),
+        "fs_dist_create": ([C.POINTER(vp), C.POINTER(DistConfig), vp], I),
+        "fs_dist_destroy": ([vp], I),
+        "fs_dist_window": ([vp, TP], I),
+        "fs_dist_info": ([vp, C.POINTER(DistInfo)], I),
+        "fs_dist_ipc_handle": ([vp, C.c_char_p], I),
+        "fs_dist_connect": ([vp, C.c_char_p], I),
+        "fs_dist_connect_local": ([vp, C.POINTER(vp)], I),
+        "fs_dist_upload": ([vp, vp, vp], I),
+        "fs_dist_download": ([vp, vp, vp, vp, vp], I),
+        "fs_dist_device_fields": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)], I),
+        "fs_dist_step": ([vp, vp, I], I),
+        "fs_dist_check": ([vp], I),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the library does not export the header's symbol

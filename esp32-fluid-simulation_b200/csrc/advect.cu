@@ -26,7 +26,7 @@ advect_gather(typename P::raw_t *__restrict__ next_p, const typename P::raw_t *_
     float si, sj;
     backtrace(si, sj, gi, gj, __ldg(vel + l), dt);
 
-    GlobalFetch<P> fetch{p, g.ox, g.oy, g.nx, g.ny, status};
+    GlobalFetch<P> fetch{p, g.ox, g.oy, g.nx, g.vx0, g.vy0, g.vx1 - g.vx0, g.vy1 - g.vy0, status};
     typename P::raw_t out[P::NC];
     sample<P>(out, fetch, si, sj, g.GX, g.GY, no_slip);
 
@@ -62,6 +62,13 @@ int launch_advect_rgb_gather(const Launch &L, uint32_t *next_c, const uint32_t *
                              const Geo &g, float dt, bool no_slip, int *status)
 {
     return launch_gather<RgbPayload>(L, next_c, c, vel, g, dt, no_slip, status);
+}
+
+int preload_advect_kernels()
+{
+    FS_PRELOAD(advect_gather<Vec2Payload>);
+    FS_PRELOAD(advect_gather<RgbPayload>);
+    return 0;
 }
 
 }  // namespace fs

@@ -109,13 +109,14 @@ __device__ __forceinline__ void backtrace(float &si, float &sj, int gi, int gj, 
 template <class P>
 struct GlobalFetch {
     const typename P::raw_t *__restrict__ base;
-    int ox, oy, nx, ny;
+    int ox, oy, nx;
+    int vx0, vy0, vw, vh;    // valid part of the window (Geo::vx0..)
     int *status;
     __device__ __forceinline__ void operator()(int gi, int gj, typename P::raw_t (&o)[P::NC]) const
     {
         const int lx = gi - ox, ly = gj - oy;
-        if ((unsigned)lx >= (unsigned)nx || (unsigned)ly >= (unsigned)ny) {
-            if (status) atomicExch(status, FS_ERR_HALO_OVERRUN);
+        if ((unsigned)(lx - vx0) >= (unsigned)vw || (unsigned)(ly - vy0) >= (unsigned)vh) {
+            if (status) atomicCAS(status, 0, FS_ERR_HALO_OVERRUN);   // the first error wins
 #pragma unroll
             for (int ch = 0; ch < P::NC; ch++) o[ch] = 0;
             return;

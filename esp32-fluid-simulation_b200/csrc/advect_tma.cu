@@ -45,13 +45,14 @@ struct TileFetch {
     const typename P::raw_t *tile;   // smem, ROW_WORDS words per row
     const typename P::raw_t *base;   // global window
     int bx0, by0;                    // local coordinate of the tile's first staged node
-    int ox, oy, nx, ny;
+    int ox, oy, nx;
+    int vx0, vy0, vw, vh;            // valid part of the window (Geo::vx0..)
     int *status;
     __device__ __forceinline__ void operator()(int gi, int gj, typename P::raw_t (&o)[P::NC]) const
     {
         const int lx = gi - ox, ly = gj - oy;
-        if ((unsigned)lx >= (unsigned)nx || (unsigned)ly >= (unsigned)ny) {  // not in this rank's window
-            if (status) atomicExch(status, FS_ERR_HALO_OVERRUN);
+        if ((unsigned)(lx - vx0) >= (unsigned)vw || (unsigned)(ly - vy0) >= (unsigned)vh) {  // not valid here
+            if (status) atomicCAS(status, 0, FS_ERR_HALO_OVERRUN);   // the first error wins
 #pragma unroll
             for (int ch = 0; ch < P::NC; ch++) o[ch] = 0;
             return;
@@ -147,11 +148,12 @@ advect_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     }
     mbar_wait(&bar, 0);
 
-    TileFetch<P> fetch{tile, reinterpret_cast<const raw_t *>(a.p), bx0, by0, g.ox, g.oy, g.nx, g.ny, a.status};
+    TileFetch<P> fetch{tile, reinterpret_cast<const raw_t *>(a.p), bx0, by0, g.ox, g.oy, g.nx,
+                       g.vx0, g.vy0, g.vx1 - g.vx0, g.vy1 - g.vy0, a.status};
     // Fast path bounds (CTA-uniform): the bilinear cell (tx..tx+1, ty..ty+1) must be staged AND inside
-    // this rank's window (outside it the hardware zero-filled the tile).
-    const int tx_lo = max(0, -bx0), tx_hi = min(TS::W - 1, g.nx - 1 - bx0);   // tx in [tx_lo, tx_hi)
-    const int ty_lo = max(0, -by0), ty_hi = min(TS::H - 1, g.ny - 1 - by0);
+    // the valid part of this rank's window (outside the window the hardware zero-filled the tile).
+    const int tx_lo = max(0, g.vx0 - bx0), tx_hi = min(TS::W - 1, g.vx1 - 1 - bx0);   // tx in [tx_lo, tx_hi)
+    const int ty_lo = max(0, g.vy0 - by0), ty_hi = min(TS::H - 1, g.vy1 - 1 - by0);
     const float x_max = (float)(g.GX - 1), y_max = (float)(g.GY - 1);
 #pragma unroll
     for (int it = 0; it < ITERS; it++) {
@@ -241,7 +243,10 @@ struct AdvDivArgs {
     float2 *v_out;
     const float2 *v_in;
     float *div;
-    Geo g;
+    Geo g;                    // compute rectangle = where the DIVERGENCE is written
+    int sx0, sy0, sx1, sy1;   // where the forced VELOCITY is stored (decomposed grids: the owned rectangle only —
+                              // the ring around it is recomputed by every rank instead of being exchanged)
+    int *status;
     float dt, two_dx_inv;
     int n_drags;
     fs_drag drags[AD_MAX_DRAGS];
@@ -269,10 +274,10 @@ advect_div_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_c
         mbar_expect_tx(&bar, ROW_WORDS * AD_H * 4);
         tma_load_2d(tile, &in_map, bx0 * 2, by0, &bar);
     }
-    TileFetch<P, AD_W, AD_H> fetch{tile, reinterpret_cast<const float *>(a.v_in), bx0, by0, g.ox, g.oy, g.nx, g.ny,
-                                   nullptr};
-    const int tx_lo = max(0, -bx0), tx_hi = min(AD_W - 1, g.nx - 1 - bx0);
-    const int ty_lo = max(0, -by0), ty_hi = min(AD_H - 1, g.ny - 1 - by0);
+    TileFetch<P, AD_W, AD_H> fetch{tile, reinterpret_cast<const float *>(a.v_in), bx0, by0, g.ox, g.oy, g.nx,
+                                   g.vx0, g.vy0, g.vx1 - g.vx0, g.vy1 - g.vy0, a.status};
+    const int tx_lo = max(0, g.vx0 - bx0), tx_hi = min(AD_W - 1, g.vx1 - 1 - bx0);
+    const int ty_lo = max(0, g.vy0 - by0), ty_hi = min(AD_H - 1, g.vy1 - 1 - by0);
     const float x_max = (float)(g.GX - 1), y_max = (float)(g.GY - 1);
     mbar_wait(&bar, 0);
 
@@ -282,7 +287,9 @@ advect_div_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_c
         const int ay = k / AD_AW, ax = k - ay * AD_AW;
         const int lx = tx0 - 1 + ax, ly = ty0 - 1 + ay;
         float out[2] = {0.f, 0.f};
-        if (lx >= 0 && lx < g.nx && ly >= 0 && ly < g.ny) {
+        // only the compute rectangle and its one-node ring (partial tiles stick out of it; on a
+        // decomposed grid nodes further out would backtrace into ghosts that were never refreshed)
+        if (lx >= max(g.x0 - 1, 0) && lx < min(g.x1 + 1, g.nx) && ly >= max(g.y0 - 1, 0) && ly < min(g.y1 + 1, g.ny)) {
             const float2 vv = *reinterpret_cast<const float2 *>(tile + (ay + AT_HALO) * ROW_WORDS + (ax + AD_LEFT - 1) * 2);
             float si, sj;
             backtrace(si, sj, g.ox + lx, g.oy + ly, vv, a.dt);
@@ -340,7 +347,7 @@ advect_div_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_c
                                   adv[ry * AD_AW + cx + 1].y, adv[(ry + 2) * AD_AW + cx + 1].y, g.ox + lx, g.oy + ly,
                                   g.GX, g.GY, a.two_dx_inv);
         const size_t l = (size_t)ly * g.nx + lx;
-        a.v_out[l] = c;
+        if (lx >= a.sx0 && lx < a.sx1 && ly >= a.sy0 && ly < a.sy1) a.v_out[l] = c;
         a.div[l] = d;
     }
 }
@@ -410,7 +417,7 @@ int launch_advect_rgb_tma(const Launch &L, uint32_t *next_c, const uint32_t *c, 
 }
 
 int launch_advect_div_tma(const Launch &L, float2 *v_out, const float2 *v_in, float *div, const fs_drag *drags_host,
-                          int n_drags, const Geo &g, float dt, float dx)
+                          int n_drags, const Geo &g, float dt, float dx, const int *store_rect, int *status)
 {
     const int w = g.x1 - g.x0, h = g.y1 - g.y0;
     if (w <= 0 || h <= 0) return 0;
@@ -420,6 +427,9 @@ int launch_advect_div_tma(const Launch &L, float2 *v_out, const float2 *v_in, fl
         return (int)cudaErrorInvalidValue;
     AdvDivArgs a;
     a.v_out = v_out; a.v_in = v_in; a.div = div; a.g = g; a.dt = dt;
+    a.sx0 = store_rect ? store_rect[0] : g.x0; a.sy0 = store_rect ? store_rect[1] : g.y0;
+    a.sx1 = store_rect ? store_rect[2] : g.x1; a.sy1 = store_rect ? store_rect[3] : g.y1;
+    a.status = status;
     a.two_dx_inv = 1.0f / (2.0f * dx);
     a.n_drags = n_drags;
     for (int k = 0; k < n_drags; k++) a.drags[k] = drags_host[k];
@@ -442,6 +452,14 @@ int launch_advect_rgb_tma_grad(const Launch &L, uint32_t *next_c, const uint32_t
                                bool no_slip, int *status)
 {
     return launch_tma<RgbPayload>(L, next_c, c, v_tmp, g, dt, no_slip, status, p, v_out, 1.0f / (2.0f * dx));
+}
+
+int preload_advect_tma_kernels()
+{
+    FS_PRELOAD(advect_tma_kernel<Vec2Payload>);
+    FS_PRELOAD(advect_tma_kernel<RgbPayload>);
+    FS_PRELOAD(advect_div_tma_kernel);
+    return 0;
 }
 
 }  // namespace fs

@@ -24,6 +24,9 @@ struct Geo {
     int ox, oy;          // global coordinate of local element (0,0)
     int nx, ny;          // local array extents; pitch = nx
     int x0, y0, x1, y1;  // compute rectangle in local coordinates, [x0,x1) x [y0,y1)
+    int vx0, vy0, vx1, vy1;  // part of the window that holds VALID data for an advect's gathers (a fetch
+                             // outside it raises FS_ERR_HALO_OVERRUN); the whole window unless a
+                             // decomposed step refreshed only part of the ghosts
 };
 
 static inline Geo geo_full(int dim_x, int dim_y)
@@ -31,6 +34,7 @@ static inline Geo geo_full(int dim_x, int dim_y)
     Geo g;
     g.GX = dim_x; g.GY = dim_y; g.ox = 0; g.oy = 0; g.nx = dim_x; g.ny = dim_y;
     g.x0 = 0; g.y0 = 0; g.x1 = dim_x; g.y1 = dim_y;
+    g.vx0 = 0; g.vy0 = 0; g.vx1 = dim_x; g.vy1 = dim_y;
     return g;
 }
 
@@ -39,6 +43,7 @@ static inline Geo geo_tile(const fs_tile &t)
     Geo g;
     g.GX = t.gdim_x; g.GY = t.gdim_y; g.ox = t.ox; g.oy = t.oy; g.nx = t.nx; g.ny = t.ny;
     g.x0 = t.x0; g.y0 = t.y0; g.x1 = t.x1; g.y1 = t.y1;
+    g.vx0 = 0; g.vy0 = 0; g.vx1 = t.nx; g.vy1 = t.ny;
     return g;
 }
 

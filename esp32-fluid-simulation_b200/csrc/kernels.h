@@ -28,9 +28,12 @@ int launch_advect_vec2f_tma(const Launch &L, float2 *next_p, const float2 *p, co
 int launch_advect_rgb_tma(const Launch &L, uint32_t *next_c, const uint32_t *c, const float2 *vel,
                           const Geo &g, float dt, bool no_slip, int *status);
 
-// fused advect velocity (no-slip) + drags + divergence over a WHOLE grid (g must be geo_full)
+// fused advect velocity (no-slip) + drags + divergence: the divergence is written on g's compute
+// rectangle (every node of it needs its 4 neighbours inside the window or beyond a global wall), the
+// forced velocity on store_rect = {x0,y0,x1,y1} in local coordinates (nullptr = the compute rectangle)
 int launch_advect_div_tma(const Launch &L, float2 *v_out, const float2 *v_in, float *div, const fs_drag *drags_host,
-                          int n_drags, const Geo &g, float dt, float dx);
+                          int n_drags, const Geo &g, float dt, float dx, const int *store_rect = nullptr,
+                          int *status = nullptr);
 int advect_div_max_drags();
 int launch_advect_rgb_tma_grad(const Launch &L, uint32_t *next_c, const uint32_t *c, float2 *v_out,
                                const float2 *v_tmp, const float *p, const Geo &g, float dt, float dx,
@@ -57,6 +60,33 @@ constexpr int SOR_BLOCKED_MAX_HALF = 16;
 int launch_sor_blocked(const Launch &L, float *p_out, const float *p_in, const float *div, const Geo &g,
                        float dx, float omega, int first_parity, int n_half, int shape, int *work_counter);
 
+// The blocked SOR pass FUSED WITH ITS HALO EXCHANGE (decomposed grids): while a tile is written
+// back, the parts of it that neighbouring ranks need as ghosts are stored straight into their
+// windows over NVLink peer memory; the CTA that finishes the last such ("rim") tile publishes the
+// exchange's sequence number in the neighbours' flag slots, and the interior tiles run on
+// underneath.  The NEXT pass waits for the neighbours' numbers before its first load.
+struct SorPushPeer {
+    float *base;             // the neighbour's p_out window (peer-mapped pointer, element (0,0))
+    int pitch;               // its window pitch in nodes
+    int dx, dy;              // local coordinate here + (dx, dy) = local coordinate there
+    int sx0, sy0, sx1, sy1;  // strip of THIS rank's rectangle it needs (local coordinates, x multiples of 4)
+};
+struct SorPushArgs {
+    int n_peers;                            // strips to push (0 = none)
+    int n_wait;                             // flags to wait for before the first load (0 = none)
+    SorPushPeer peer[8];
+    unsigned long long *signal[8];          // flag slots in the neighbours' arenas, one per peer
+    unsigned long long *wait[8];            // this rank's flag slots
+    unsigned long long seq_signal, seq_wait, timeout_ns;
+    int has_l, has_r, has_d, has_u;         // sides of the rectangle that face another rank
+    int rim_total;                          // tiles whose region crosses such a side (filled by the launcher)
+    int *rim_done;                          // device counter, zeroed before the launch
+    int *status;                            // raised to FS_ERR_HALO_TIMEOUT when a neighbour never signals
+};
+int launch_sor_blocked_push(const Launch &L, float *p_out, const float *p_in, const float *div, const Geo &g,
+                            float dx, float omega, int first_parity, int n_half, int shape, int *work_counter,
+                            SorPushArgs &push, int grid_limit);
+
 // ensemble.cu — whole loop() body per grid, resident in shared memory
 size_t ensemble_smem_bytes(int dim_x, int dim_y);
 bool ensemble_supported(int dim_x, int dim_y, size_t max_smem_optin);
@@ -77,6 +107,7 @@ struct HaloCopy {
     const uint32_t *src;      // this rank's window
     uint32_t *dst;            // a neighbour's ghost region (peer pointer)
     int src_pitch_words, dst_pitch_words, row_words, rows;
+    int vec16;                // filled by the launcher: everything is 16-byte aligned
 };
 struct HaloArgs {
     HaloCopy copies[HALO_MAX_COPIES];
@@ -88,6 +119,21 @@ struct HaloArgs {
     int n_copies, n_peers;
 };
 int launch_halo_exchange(const Launch &L, HaloArgs &a, unsigned int *done_counter, int *status);
+
+// Load every kernel a decomposed step can launch (see FS_PRELOAD below): returns a cudaError_t.
+int preload_advect_kernels();
+int preload_advect_tma_kernels();
+int preload_stencil_kernels();
+int preload_sor_kernels();
+int preload_sor_blocked_kernels();
+int preload_halo_kernels();
+int preload_upscale_kernels();
+#define FS_PRELOAD(k)                                                        \
+    do {                                                                     \
+        cudaFuncAttributes fa;                                               \
+        cudaError_t pe = cudaFuncGetAttributes(&fa, k);                      \
+        if (pe != cudaSuccess) return (int)pe;                               \
+    } while (0)
 
 // upscale.cu — ino:116-177
 int launch_upscale4_rgb565(const Launch &L, uint16_t *out, const uint32_t *c, int dim_x, int dim_y);

@@ -114,4 +114,11 @@ int launch_sor_half_sweep(const Launch &L, float *p, const float *div, const Geo
     return (int)cudaGetLastError();
 }
 
+int preload_sor_kernels()
+{
+    FS_PRELOAD(sor_half_sweep_kernel);
+    FS_PRELOAD(sor_residual_kernel);
+    return 0;
+}
+
 }  // namespace fs

@@ -151,28 +151,80 @@ __device__ __forceinline__ void sweep_pass(float (&p)[R][4], const float (&dxd)[
     }
 }
 
-// write back the tile interior, clipped to the compute rectangle
-template <int R>
+// write back the tile interior, clipped to the compute rectangle; with PUSH, also straight into the
+// ghost regions of the neighbouring ranks that need it (peer memory, 16-byte stores)
+template <int R, bool PUSH = false>
 __device__ __forceinline__ void store_tile(const float (&p)[R][4], const BlockedArgs &a, float *p_out, int rlx0,
-                                           int rly0, int lx0, int ly0)
+                                           int rly0, int lx0, int ly0, const SorPushArgs *push = nullptr)
 {
     const Geo &g = a.g;
     const int ox0 = max(rlx0 + a.hpx, g.x0), ox1 = min(rlx0 + a.hpx + a.tw_out, g.x1);
     const int oy0 = max(rly0 + a.hpy, g.y0), oy1 = min(rly0 + a.hpy + a.th_out, g.y1);
     const bool cols_full = lx0 >= ox0 && lx0 + 3 < ox1;
+    unsigned peers = 0;                                     // CTA-uniform: strips this tile's output meets
+    if constexpr (PUSH) {
+        for (int k = 0; k < push->n_peers; k++) {
+            const SorPushPeer &q = push->peer[k];
+            if (ox0 < q.sx1 && ox1 > q.sx0 && oy0 < q.sy1 && oy1 > q.sy0) peers |= 1u << k;
+        }
+    }
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int ly = ly0 + r;
         if (ly < oy0 || ly >= oy1) continue;
         float *row = p_out + (size_t)ly * g.nx;
         if (cols_full && a.vec_ok) {
-            *reinterpret_cast<float4 *>(row + lx0) = make_float4(p[r][0], p[r][1], p[r][2], p[r][3]);
+            const float4 val = make_float4(p[r][0], p[r][1], p[r][2], p[r][3]);
+            *reinterpret_cast<float4 *>(row + lx0) = val;
+            if constexpr (PUSH) {
+                for (unsigned m = peers; m; m &= m - 1) {
+                    const SorPushPeer &q = push->peer[__ffs(m) - 1];
+                    if (ly >= q.sy0 && ly < q.sy1 && lx0 >= q.sx0 && lx0 < q.sx1)
+                        *reinterpret_cast<float4 *>(q.base + (size_t)(ly + q.dy) * q.pitch + (lx0 + q.dx)) = val;
+                }
+            }
         } else {
 #pragma unroll
             for (int c = 0; c < 4; c++)
                 if (lx0 + c >= ox0 && lx0 + c < ox1) row[lx0 + c] = p[r][c];
         }
     }
+}
+
+// a tile is a RIM tile when its region crosses a side of the rectangle that faces another rank:
+// it reads ghosts and/or produces values a neighbour needs (CTA-uniform; same test on the host)
+template <int R, int NW>
+__host__ __device__ __forceinline__ bool region_is_rim(const Geo &g, const SorPushArgs &q, int rlx0, int rly0)
+{
+    return (q.has_l && rlx0 < g.x0) || (q.has_r && rlx0 + BLK_RW > g.x1) || (q.has_d && rly0 < g.y0) ||
+           (q.has_u && rly0 + R * NW > g.y1);
+}
+
+__device__ __forceinline__ unsigned long long halo_global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// one thread: wait until every neighbour's flag carries `seq` (their strips are in our ghosts)
+__device__ __forceinline__ void wait_for_neighbours(const SorPushArgs &q)
+{
+    const unsigned long long t0 = halo_global_ns();
+    for (int k = 0; k < q.n_wait; k++) {
+        if (q.status && *reinterpret_cast<volatile int *>(q.status) == FS_ERR_HALO_TIMEOUT) break;   // already given up
+        for (;;) {
+            unsigned long long seen;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(q.wait[k]) : "memory");
+            if (seen >= q.seq_wait) break;
+            if (q.timeout_ns && halo_global_ns() - t0 > q.timeout_ns) {
+                if (q.status) atomicExch(q.status, FS_ERR_HALO_TIMEOUT);
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");   // the neighbours' generic stores -> this CTA's TMA reads
 }
 
 // Work order of the persistent kernel: the frame of tiles along the window's edge first (they
@@ -262,10 +314,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) sor_blocked_kernel(const Blocke
 // ---- loader 2: persistent CTAs, next tile prefetched into shared memory by TMA -----------------
 // The hardware zero-fills the parts of a region outside the window — exactly what loader 1 does by
 // hand.
-template <int R, int NW, int MINB>
-__global__ void __launch_bounds__(32 * NW, MINB)
-sor_blocked_tma_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant__ CUtensorMap d_map,
-                       const BlockedArgs a, int ntx, int nty, int *work_counter)
+template <int R, int NW, int MINB, bool PUSH>
+__device__ __forceinline__ void sor_blocked_tma_body(const CUtensorMap &p_map, const CUtensorMap &d_map,
+                                                     const BlockedArgs &a, int ntx, int nty, int *work_counter,
+                                                     const SorPushArgs *push)
 {
     constexpr int RH = R * NW;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -303,6 +355,9 @@ sor_blocked_tma_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_c
     asm volatile("griddepcontrol.wait;" ::: "memory");
     int ahead = n_tiles;                       // thread 0 only: the ticket drawn one tile early
     if (threadIdx.x == 0) {
+        if constexpr (PUSH) {
+            if (push->n_wait > 0) wait_for_neighbours(*push);   // p_in's ghosts are the neighbours' previous pass
+        }
         const int first = atomicAdd(work_counter, 1);
         s_tile[0] = first;
         prefetch(first);
@@ -344,8 +399,40 @@ sor_blocked_tma_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_c
             ahead = atomicAdd(work_counter, 1);   // consumed one tile later
         }
         sweep_region<R, NW>(p, dxd, a, mail, rlx0, rly0, gi0, gj0, a.n_half);
-        store_tile<R>(p, a, a.p_out, rlx0, rly0, lx0, ly0);
+        store_tile<R, PUSH>(p, a, a.p_out, rlx0, rly0, lx0, ly0, push);
+        if constexpr (PUSH) {
+            if (push->n_peers > 0 && region_is_rim<R, NW>(g, *push, rlx0, rly0)) {
+                // publish: the CTA that completes the LAST rim tile tells every neighbour that this
+                // rank's strips are in their ghosts — interior tiles keep running underneath
+                __threadfence_system();
+                __syncthreads();
+                if (threadIdx.x == 0 && atomicAdd(push->rim_done, 1) == push->rim_total - 1) {
+                    __threadfence_system();
+                    for (int k = 0; k < push->n_peers; k++)
+                        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(push->signal[k]), "l"(push->seq_signal)
+                                     : "memory");
+                }
+            }
+        }
     }
+}
+
+template <int R, int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB)
+sor_blocked_tma_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant__ CUtensorMap d_map,
+                       const BlockedArgs a, int ntx, int nty, int *work_counter)
+{
+    sor_blocked_tma_body<R, NW, MINB, false>(p_map, d_map, a, ntx, nty, work_counter, nullptr);
+}
+
+// the same pass fused with its halo exchange (decomposed grids; see SorPushArgs in kernels.h)
+template <int R, int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB)
+sor_blocked_push_kernel(const __grid_constant__ CUtensorMap p_map, const __grid_constant__ CUtensorMap d_map,
+                        const BlockedArgs a, int ntx, int nty, int *work_counter,
+                        const __grid_constant__ SorPushArgs push)
+{
+    sor_blocked_tma_body<R, NW, MINB, true>(p_map, d_map, a, ntx, nty, work_counter, &push);
 }
 
 // ---- loader 3: the WHOLE solve in one persistent launch ------------------------------------------
@@ -554,6 +641,46 @@ static int launch_cfg_tma(const Launch &L, BlockedArgs &a, int *work_counter)
 }
 
 template <int R, int NW, int MINB>
+static int launch_cfg_push(const Launch &L, BlockedArgs &a, int *work_counter, SorPushArgs &push, int grid_limit)
+{
+    const Geo &g = a.g;
+    int ntx, nty;
+    if (!tile_cfg<R, NW>(a, ntx, nty)) return (int)cudaErrorInvalidValue;
+    if (ntx <= 0 || nty <= 0) return (int)cudaErrorInvalidValue;   // an empty rectangle cannot take part in an exchange
+    CUtensorMap p_map, d_map;
+    if (!tma_make_map_2d(&d_map, a.div, g.nx, g.ny, g.nx, BLK_RW, R * NW)) return (int)cudaErrorInvalidValue;
+    p_map = d_map;
+    if (a.p_in && !tma_make_map_2d(&p_map, a.p_in, g.nx, g.ny, g.nx, BLK_RW, R * NW))
+        return (int)cudaErrorInvalidValue;
+    // rim tiles: same test as the kernel's
+    push.rim_total = 0;
+    for (int ty = 0; ty < nty; ty++)
+        for (int tx = 0; tx < ntx; tx++)
+            push.rim_total += region_is_rim<R, NW>(g, push, a.lax + tx * a.tw_out - a.hpx, a.lay + ty * a.th_out - a.hpy);
+    if (push.n_peers > 0 && push.rim_total == 0) return (int)cudaErrorInvalidValue;
+    const size_t smem = (size_t)2 * R * NW * BLK_RW * 4 + sizeof(float4) * 2 * NW * 2 * 32;
+    cudaError_t e = cudaFuncSetAttribute(sor_blocked_push_kernel<R, NW, MINB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int n_tiles = ntx * nty;
+    int grid = n_tiles < MINB * L.num_sms ? n_tiles : MINB * L.num_sms;
+    if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(32 * NW);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = L.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, sor_blocked_push_kernel<R, NW, MINB>, p_map, d_map, a, ntx, nty, work_counter, push);
+    ++*L.launches;
+    return (int)e;
+}
+
+template <int R, int NW, int MINB>
 static int launch_solve_cfg(const Launch &L, SolveArgs &sa)
 {
     BlockedArgs &a = sa.a;
@@ -658,6 +785,42 @@ int launch_sor_blocked(const Launch &L, float *p_out, const float *p_in, const f
             return tma_ok ? launch_cfg_tma<16, 12, 1>(L, a, work_counter) : launch_cfg<12, 16, 1>(L, a);
         default: return launch_cfg<12, 8, 2>(L, a);  // 128 x 96 region, two CTAs per SM
     }
+}
+
+// One blocked pass fused with its halo exchange (see SorPushArgs).  Needs the TMA loader: 16-byte
+// aligned rows and pointers (decomposed windows always are); shapes 3 and 5.
+int launch_sor_blocked_push(const Launch &L, float *p_out, const float *p_in, const float *div, const Geo &g,
+                            float dx, float omega, int first_parity, int n_half, int shape, int *work_counter,
+                            SorPushArgs &push, int grid_limit)
+{
+    if (g.x1 <= g.x0 || g.y1 <= g.y0 || n_half <= 0 || n_half > SOR_BLOCKED_MAX_HALF) return (int)cudaErrorInvalidValue;
+    BlockedArgs a;
+    a.p_out = p_out;
+    a.p_in = p_in;
+    a.div = div;
+    a.g = g;
+    a.k = make_sor_coef(dx, omega);
+    a.first_parity = first_parity & 1;
+    a.n_half = n_half;
+    a.vec_ok = (g.nx % 4 == 0) && ((uintptr_t)p_out % 16 == 0) && ((uintptr_t)div % 16 == 0) &&
+               (!p_in || (uintptr_t)p_in % 16 == 0);
+    if (!a.vec_ok || !work_counter || tma_encode_fn() == nullptr) return (int)cudaErrorInvalidValue;
+    for (int k = 0; k < push.n_peers; k++) {
+        const SorPushPeer &q = push.peer[k];
+        if ((q.sx0 | q.sx1 | q.dx | q.pitch) & 3 || (uintptr_t)q.base % 16) return (int)cudaErrorInvalidValue;
+    }
+    if (push.n_peers > 0 && ((g.x0 | g.x1) & 3)) return (int)cudaErrorInvalidValue;
+    return shape == 5 ? launch_cfg_push<10, 16, 1>(L, a, work_counter, push, grid_limit)
+                      : launch_cfg_push<12, 16, 1>(L, a, work_counter, push, grid_limit);
+}
+
+int preload_sor_blocked_kernels()
+{
+    FS_PRELOAD((sor_blocked_push_kernel<12, 16, 1>));
+    FS_PRELOAD((sor_blocked_push_kernel<10, 16, 1>));
+    FS_PRELOAD((sor_blocked_tma_kernel<12, 16, 1>));
+    FS_PRELOAD((sor_blocked_kernel<12, 16, 1>));
+    return 0;
 }
 
 }  // namespace fs

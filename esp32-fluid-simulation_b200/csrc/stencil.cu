@@ -277,4 +277,15 @@ int launch_max_displacement(const Launch &L, unsigned int *out_bits, const float
     return (int)cudaGetLastError();
 }
 
+int preload_stencil_kernels()
+{
+    FS_PRELOAD(divergence_kernel);
+    FS_PRELOAD(divergence_x4_kernel);
+    FS_PRELOAD(subtract_gradient_kernel);
+    FS_PRELOAD(subtract_gradient_x4_kernel);
+    FS_PRELOAD(apply_drags_kernel);
+    FS_PRELOAD(max_displacement_kernel);
+    return 0;
+}
+
 }  // namespace fs

@@ -95,4 +95,10 @@ int launch_upscale4_rgb565(const Launch &L, uint16_t *out, const uint32_t *c, in
     return (int)cudaGetLastError();
 }
 
+int preload_upscale_kernels()
+{
+    FS_PRELOAD(upscale4_rgb565_kernel);
+    return 0;
+}
+
 }  // namespace fs

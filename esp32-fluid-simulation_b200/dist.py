@@ -436,6 +436,111 @@ class PeerComm:
             self.ops.ctx.ipc_close(p)
 
 
+class NativeDist:
+    """One rank of a decomposed grid behind the C ABI (fs_dist_*, csrc/dist.cu): the whole decomposed
+    loop() body — fused advect+drags+divergence on the grown rectangle, blocked SOR passes fused with
+    their NVLink halo exchange, gradient-subtract, one velocity+dye exchange kernel, dye advect — is
+    sequenced in C++; Python only ships the IPC handles and the drag records."""
+
+    def __init__(self, ctx, gdim_x: int, gdim_y: int, world: int, rank: int, iters: int, ghost: int = 64,
+                 advect_halo: int = 40, grid: tuple[int, int] | None = None,
+                 dt=np.float32(1 / 30.0), dx=np.float32(1.0), omega=np.float32(1.96)):
+        import ctypes as C
+
+        from . import _lib
+        self._C, self._lib, self.ctx = C, _lib, ctx
+        self._L = _lib.lib()
+        px, py = grid or (0, 0)
+        cfg = _lib.DistConfig(gdim_x, gdim_y, world, rank, px, py, ghost, advect_halo, iters, float(dt), float(dx),
+                              float(omega))
+        h = C.c_void_p()
+        _lib.check(self._L.fs_dist_create(C.byref(h), C.byref(cfg), ctx._h), "fs_dist_create")
+        self._h = h
+        t = _lib.Tile()
+        _lib.check(self._L.fs_dist_window(self._h, C.byref(t)), "fs_dist_window")
+        self.window = Window(t.gdim_x, t.gdim_y, t.ox, t.oy, t.nx, t.ny, t.x0, t.y0, t.x1, t.y1)
+        self.world, self.rank = world, rank
+
+    def close(self):
+        if getattr(self, "_h", None):
+            if getattr(self.ctx, "_h", None):      # the context must outlive its fs_dist (else: leak, not crash)
+                self._L.fs_dist_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    @property
+    def info(self) -> dict:
+        i = self._lib.DistInfo()
+        self._lib.check(self._L.fs_dist_info(self._h, self._C.byref(i)), "fs_dist_info")
+        return {n: getattr(i, n) for n, _ in i._fields_}
+
+    def ipc_handle(self) -> bytes:
+        buf = self._C.create_string_buffer(64)
+        self._lib.check(self._L.fs_dist_ipc_handle(self._h, buf), "fs_dist_ipc_handle")
+        return buf.raw
+
+    def connect(self, handles: list[bytes]):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        self._lib.check(self._L.fs_dist_connect(self._h, blob), "fs_dist_connect")
+
+    def connect_local(self, ranks: list["NativeDist"]):
+        arr = (self._C.c_void_p * self.world)(*[r._h.value for r in ranks])
+        self._lib.check(self._L.fs_dist_connect_local(self._h, arr), "fs_dist_connect_local")
+
+    @staticmethod
+    def _addr(a):
+        if type(a).__module__.startswith("torch"):
+            assert a.is_contiguous()
+            return a.data_ptr()
+        assert a.flags.c_contiguous
+        return a.ctypes.data
+
+    def upload(self, v_window, c_window):
+        """Whole windows [ny, nx, 2] float32 / [ny, nx, 3] uint32 (numpy, pinned or device tensors)."""
+        w = self.window
+        assert tuple(v_window.shape) == (w.ny, w.nx, 2) and tuple(c_window.shape) == (w.ny, w.nx, 3)
+        self._lib.check(self._L.fs_dist_upload(self._h, self._addr(v_window), self._addr(c_window)), "fs_dist_upload")
+
+    def download(self, fields="vcpd", out=None) -> dict:
+        """The owned rectangle of the current state (numpy; synchronises)."""
+        w = self.window
+        h, wd = w.y1 - w.y0, w.x1 - w.x0
+        res = out or {}
+        if "v" in fields and "v" not in res:
+            res["v"] = np.empty((h, wd, 2), np.float32)
+        if "c" in fields and "c" not in res:
+            res["c"] = np.empty((h, wd, 3), np.uint32)
+        if "p" in fields and "p" not in res:
+            res["p"] = np.empty((h, wd), np.float32)
+        if "d" in fields and "d" not in res:
+            res["d"] = np.empty((h, wd), np.float32)
+        ptr = lambda k: self._addr(res[k]) if k in fields else None   # noqa: E731
+        self._lib.check(self._L.fs_dist_download(self._h, ptr("v"), ptr("c"), ptr("p"), ptr("d")), "fs_dist_download")
+        return res
+
+    def device_fields(self):
+        """Addresses of the CURRENT device windows (v, c, p, div)."""
+        C = self._C
+        v, c, p, d = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._lib.check(self._L.fs_dist_device_fields(self._h, C.byref(v), C.byref(c), C.byref(p), C.byref(d)),
+                        "fs_dist_device_fields")
+        return v.value, c.value, p.value, d.value
+
+    def step(self, drags=None):
+        from .ops import _drags
+        d, n = _drags(drags)
+        self._lib.check(self._L.fs_dist_step(self._h, d.ctypes.data if n else None, n), "fs_dist_step")
+
+    def check(self):
+        self._lib.check(self._L.fs_dist_check(self._h), "fs_dist_check")
+
+
 def max_window_nodes(gdim_x, gdim_y, world, ghost, grid=None) -> int:
     return max(d.window.nx * d.window.ny
                for d in (Decomposition(gdim_x, gdim_y, world, r, ghost, grid) for r in range(world)))
@@ -445,8 +550,238 @@ def max_window_nodes(gdim_x, gdim_y, world, ghost, grid=None) -> int:
 # bench.py's N>1 leg
 # ---------------------------------------------------------------------------------------
 
+def _device_view(ptr, shape, typestr):
+    class _V:
+        pass
+    v = _V()
+    v.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+    return v
+
+
 def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
-    """Weak scaling: every GPU owns tile_edge x tile_edge nodes of one global grid."""
+    """bench.py's N>1 arm.  Weak scaling: every GPU owns tile_edge x tile_edge nodes of one global grid
+    (or --global-grid: a fixed global grid).  Default path: fs_dist_* (the decomposed step sequenced in
+    C++, SOR passes fused with their NVLink halo exchange).  FS_HALO=nccl / peer-py select the
+    Python-sequenced comparison paths."""
+    import os
+    import sys
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    import esp32_fluid_simulation_b200 as fb
+
+    from . import synth
+    mode = os.environ.get("FS_HALO", "native")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
+    px, py = process_grid(world)
+    gx, gy = tile_edge * px, tile_edge * py
+    scaling = "weak"
+    if getattr(args, "global_grid", ""):
+        gx, gy = (int(t) for t in args.global_grid.lower().split("x"))
+        scaling = "strong"
+    ghost, halo = 64, 40      # +-1000 nodes/s synthetic drags move a node 34 cells; A = 40 leaves D + 1 = 17 for the SOR ring
+    if mode == "native":
+        # every rank must end up on the same path: agree on whether CUDA IPC works everywhere
+        ok, why = 1, ""
+        try:
+            probe = fb.Context(local_rank, torch.cuda.current_stream(dev))
+            base = probe.arena_alloc(1 << 20)
+            handle = probe.ipc_export(base)
+        except Exception as e:  # noqa: BLE001 — e.g. CUDA IPC not permitted in this container
+            ok, why, handle, base = 0, f"{type(e).__name__}: {e}", None, None
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        if ok:
+            try:
+                peer = (rank + 1) % world
+                probe.ipc_close(probe.ipc_open(handles[peer]))
+            except Exception as e:  # noqa: BLE001
+                ok, why = 0, f"{type(e).__name__}: {e}"
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.barrier()
+        if base is not None:
+            probe.arena_free(base)
+        if int(flag.item()) == 0:
+            if rank == 0:
+                print(f"[bench] peer-memory halos unavailable ({why or 'another rank failed'}); using NCCL send/recv",
+                      file=sys.stderr, flush=True)
+            mode = "nccl"
+    if mode != "native":
+        return bench_decomposed_python(args, tile_edge, iters, n_drags, mode)
+
+    parity = None
+    verify = getattr(args, "verify_fn", None)        # bench.py's untimed parity leg (it owns the CPU checker)
+    if verify is not None and not getattr(args, "no_verify", False):
+        parity = verify(fb, torch, dist, local_rank, world, rank, gx, gy, iters, ghost, halo, n_drags)
+        if not (parity["oracle_small"] and parity["one_gpu_equals_n"]):
+            if rank == 0:
+                print(f"[bench] PARITY FAILURE in the decomposed path: {parity}", file=sys.stderr, flush=True)
+            dist.barrier()
+            raise SystemExit(4)
+
+    ctx = fb.Context(local_rank, torch.cuda.current_stream(dev))
+    sor_t = ctx.get_option("sor_t")
+    sim = NativeDist(ctx, gx, gy, world, rank, iters, ghost=ghost, advect_halo=halo, dt=synth.DT, dx=synth.DX,
+                     omega=synth.OMEGA)
+    handles = [None] * world
+    dist.all_gather_object(handles, sim.ipc_handle())
+    sim.connect(handles)
+    w = sim.window
+    hv = torch.from_numpy(synth.velocity(gx, gy, window=(w.ox, w.oy, w.nx, w.ny))).pin_memory()
+    hc = torch.from_numpy(synth.dye(gx, gy, window=(w.ox, w.oy, w.nx, w.ny)).view(np.int32)).pin_memory()
+    sim.upload(hv, hc)
+    drags = [synth.drags(gx, gy, s, n=n_drags) for s in range(args.warmup + args.steps)]
+    frame = None
+    if getattr(args, "upscale", False):
+        # the rank's part of the 4x RGB565 frame (ino:116-177): upscale the window, ghosts included
+        frame = torch.empty((w.nx - 1) * 4, (w.ny - 1) * 4, dtype=torch.int16, device=dev)
+
+    def dye_window():
+        return torch.as_tensor(_device_view(sim.device_fields()[1], (w.ny, w.nx, 3), "<i4"), device=dev)
+
+    def one_step(k):
+        sim.step(drags[k])
+        if frame is not None:
+            ctx.upscale4_rgb565(frame, dye_window(), w.nx, w.ny)
+
+    for s in range(args.warmup):
+        one_step(s)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    launches0, ex0 = ctx.launch_count, sim.info["exchanges"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = getattr(args, "clock_sampler", None)
+    clk = sampler(local_rank).__enter__() if (sampler and rank == 0) else None
+    t0 = time.perf_counter()
+    e0.record()
+    for s in range(args.warmup, args.warmup + args.steps):
+        one_step(s)
+    e1.record()
+    torch.cuda.synchronize()
+    info = sim.info
+    launches, exchanges = ctx.launch_count - launches0, info["exchanges"] - ex0
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    pv, pc, pp, pd = sim.device_fields()
+    f_v = torch.as_tensor(_device_view(pv, (w.ny, w.nx, 2), "<f4"), device=dev)
+    f_d = torch.as_tensor(_device_view(pd, (w.ny, w.nx), "<f4"), device=dev)
+    f_p = torch.as_tensor(_device_view(pp, (w.ny, w.nx), "<f4"), device=dev)
+    f_p2 = torch.empty_like(f_p)
+    tile = fb.Tile(w.gdim_x, w.gdim_y, w.ox, w.oy, w.nx, w.ny, w.x0, w.y0, w.x1, w.y1)
+    if clk is not None:
+        t_busy = time.time() + 0.3          # keep the device busy so the 100 ms sampler sees loaded clocks
+        while time.time() < t_busy:
+            ctx.tile_calculate_divergence(f_p2, f_v, tile, synth.DX)
+        torch.cuda.synchronize()
+        clk.__exit__(None, None, None)
+    clocks = clk.summary() if clk is not None else None
+    sim.check()                  # no advect of the timed region left its halo, no hand-shake timed out
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1), wall_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0].item()) / args.steps
+    nodes = gx * gy
+    value = nodes / (ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (the SOR passes), per GPU, local compute only ----
+    roofline = None
+    try:
+        plan = [min(sor_t, iters - k) for k in range(0, iters, sor_t)]
+
+        def local_solve():
+            src, dst = None, f_p
+            for tt in plan:
+                ctx.tile_sor_sweeps(dst, src, f_d, tile, synth.DX, synth.OMEGA, 0, 2 * tt)
+                src, dst = dst, (f_p2 if dst is f_p else f_p)
+
+        for _ in range(2):
+            local_solve()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        r0.record()
+        for _ in range(reps):
+            local_solve()
+        r1.record()
+        torch.cuda.synchronize()
+        sor_ms = r0.elapsed_time(r1) / reps
+        own = (w.x1 - w.x0) * (w.y1 - w.y0)
+        peak = 6650.0
+        try:
+            import json as _json
+            peak = float(_json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                        "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:  # noqa: BLE001
+            pass
+        achieved = 12.0 * own * iters / (sor_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "ms": sor_ms, "launches_per_solve": len(plan),
+                    "kernel": "sor_blocked_tma_kernel on this rank's window (rank 0; the passes of one solve without "
+                              "the halo exchange fused in); algorithmic 12 B/node-iteration",
+                    "sor_share_of_step": sor_ms / ms}
+    except Exception as e:  # noqa: BLE001 — never let the extra measurement take the bench line down
+        roofline = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- e2e: every rank's state starts and ends in pinned HOST memory, every step ----
+    own_h, own_w = w.y1 - w.y0, w.x1 - w.x0
+    ov = torch.empty((own_h, own_w, 2), dtype=torch.float32).pin_memory()
+    oc = torch.empty((own_h, own_w, 3), dtype=torch.int32).pin_memory()
+    e2e_steps = 3
+
+    def e2e_step(k):
+        sim.upload(hv, hc)                          # H2D: this rank's window of the state
+        one_step(k % len(drags))
+        self_out = {"v": ov.numpy(), "c": oc.numpy().view(np.uint32)}
+        sim.download("vc", out=self_out)            # D2H: the rectangle this rank owns (synchronises)
+
+    e2e_step(0)
+    dist.barrier()
+    t1 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    dist.barrier()
+    te = torch.tensor([(time.perf_counter() - t1) / e2e_steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    sim.check()
+    e2e_s = float(te.item())
+    own_nodes = own_h * own_w
+    e2e = {"value": nodes / e2e_s / 1e6, "unit": "Mcell-steps/s", "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "h2d_bytes_per_step": int(w.nx * w.ny * 20 + 12 * n_drags) * world,
+           "d2h_bytes_per_step": int(own_nodes * 20) * world,
+           "api": "fs_dist_upload (pinned host window -> device) + fs_dist_step + fs_dist_download (owned rectangle -> "
+                  "pinned host), every rank"}
+    result = {
+        "metric": "Mcell-steps/s (advect+project, 50 SOR iters) at 4096^2", "value": value,
+        "unit": "Mcell-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f32+uq32", "data": "synthetic",
+        "config": {"workload": f"{gx}x{gy} grid block-decomposed {px}x{py}, {own_w}x{own_h} nodes per GPU, "
+                               f"{iters} SOR iterations, velocity + dye advection"
+                               + (", 4x RGB565 frame every step" if frame is not None else ""),
+                   "grid": [gx, gy], "process_grid": [px, py], "ghost": ghost, "sor_t": sor_t,
+                   "halo": "fs_dist (C++): SOR passes fused with their NVLink peer-store halo exchange; one exchange "
+                           "kernel for velocity + dye",
+                   "static_advect_halo": halo, "velocity_halo": info["velocity_halo"], "dye_halo": info["dye_halo"],
+                   "div_ring": info["div_ring"],
+                   "halo_exchanges_per_step": exchanges / args.steps,
+                   "l2": "per-GPU state exceeds the 126 MB L2; no flush needed",
+                   "timing": "CUDA events on the compute stream, max over ranks"},
+        "wall_ms_per_step_max": float(t[1].item()) / args.steps,
+        "gpu_launches": int(launches),
+        "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": None, "parity": parity,
+    }
+    sim.close()
+    return result
+
+
+def bench_decomposed_python(args, tile_edge: int, iters: int, n_drags: int, mode: str) -> dict:
+    """The Python-sequenced decomposed step (DecomposedSim): NCCL send/recv halos (mode "nccl", kept for
+    comparison) or one stand-alone peer-memory exchange kernel per exchange (mode "peer-py")."""
     import os
     import sys
     import time
@@ -465,7 +800,7 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
         scaling = "strong"
     dev = torch.device("cuda", local_rank)
     ghost = 64
-    mode = os.environ.get("FS_HALO", "peer")        # peer = NVLink stores (default), nccl = send/recv
+    mode = "peer" if mode == "peer-py" else mode
     dec = Decomposition(gx, gy, world, rank, ghost=ghost)
     ops = comm = None
     if mode == "peer":

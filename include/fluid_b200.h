@@ -77,7 +77,9 @@ int  fs_ctx_synchronize(fs_ctx *ctx);
  *   "advect" : 0 = direct L1/L2 gather, 1 = TMA-staged shared-memory tile (default where legal)
  *   "fuse"   : bit mask for fs_step: 1 = drags + divergence folded into the velocity advect, 2 =
  *              gradient-subtract folded into the dye advect (measured slower than the stand-alone
- *              gradient kernel, which runs at the HBM roofline); 0 = one kernel per operator; default 1 */
+ *              gradient kernel, which runs at the HBM roofline); 0 = one kernel per operator; default 1
+ *   "sor_grid_limit": cap on the persistent SOR grid, 0 (default) = one CTA per SM; used when several
+ *              emulated ranks share one device */
 int  fs_ctx_set_option(fs_ctx *ctx, const char *name, int value);
 int  fs_ctx_get_option(fs_ctx *ctx, const char *name, int *value);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
@@ -230,6 +232,59 @@ int fs_halo_exchange(const fs_halo_copy *copies, int n_copies, void *const *sign
                      void *const *wait_flags, int n_peers, unsigned long long seq, fs_ctx *ctx);
 /* Re-target the context at another stream (e.g. a capturing stream). */
 int fs_ctx_set_stream(fs_ctx *ctx, void *stream);
+
+
+/* ---- the decomposed step as ONE object per rank (fs_dist_*) -----------------------
+ * fs_dist owns a rank's windows of every field (one IPC-exportable arena), knows its neighbours and
+ * runs the whole loop() body (ino:249-289) of its rectangle per call:
+ *   fused advect+drags+divergence on the rectangle grown by the SOR passes' redundancy ring  ->
+ *   blocked SOR passes, each FUSED with its halo exchange (rim tiles store straight into the
+ *   neighbours' ghosts over NVLink, interior tiles overlap the hand-shake)  ->  gradient-subtract  ->
+ *   one exchange kernel for projected velocity + dye  ->  dye advect.
+ * Results are bit-identical to fs_step on the whole grid.  Every rank must make the same calls.
+ * Bootstrap: create on every rank, exchange the 64-byte fs_dist_ipc_handle()s by any means
+ * (torch.distributed, MPI, a file), fs_dist_connect() with all `world` handles in rank order. */
+typedef struct fs_dist fs_dist;
+typedef struct fs_dist_config {
+    int gdim_x, gdim_y;     /* global grid */
+    int world, rank;
+    int px, py;             /* ranks along dim_x / dim_y; 0 = choose (1x1, 1x2, 2x2, 2x4) */
+    int ghost;              /* ghost nodes towards each neighbouring rank, multiple of 4 (64) */
+    int advect_halo;        /* A: how far (nodes) a backtrace may leave the rectangle; beyond it the
+                               step raises FS_ERR_HALO_OVERRUN.  Needs A + 2*sor_t + 2 <= ghost */
+    int iters;              /* SOR iterations per step (the context's "sor_t" of them per pass) */
+    float dt, dx, omega;
+} fs_dist_config;
+typedef struct fs_dist_info_t {
+    int px, py, n_neighbours;
+    int sor_passes, sor_t;
+    int div_ring;           /* the divergence is formed on the rectangle grown by this many nodes */
+    int velocity_halo, dye_halo;   /* ghost widths refreshed every step */
+    int exchanges_per_step;
+    unsigned long long exchanges;  /* hand-shakes since creation */
+    size_t arena_bytes;
+} fs_dist_info_t;
+int fs_dist_create(fs_dist **out, const fs_dist_config *cfg, fs_ctx *ctx);
+int fs_dist_destroy(fs_dist *d);
+int fs_dist_window(const fs_dist *d, fs_tile *out);          /* this rank's window (pitch = nx) */
+int fs_dist_info(const fs_dist *d, fs_dist_info_t *out);
+int fs_dist_ipc_handle(fs_dist *d, unsigned char handle[64]);
+/* `handles`: world x 64 bytes, rank order; maps the (up to 8) neighbours' arenas */
+int fs_dist_connect(fs_dist *d, const unsigned char *handles);
+/* all ranks live in THIS process on one device (tests, single-GPU emulation): plain pointers */
+int fs_dist_connect_local(fs_dist *d, fs_dist *const *all_ranks);
+/* whole windows (nx*ny elements, ghosts included; their contents are refreshed before use), host or
+ * device pointers; asynchronous on the context's stream */
+int fs_dist_upload(fs_dist *d, const fs_vec2f *v_window, const fs_rgb_uq32 *c_window);
+/* the OWNED rectangle of the current state as dense (x1-x0) x (y1-y0) arrays (host or device
+ * pointers; any may be NULL); p/div = the last step's pressure and divergence.  Synchronises. */
+int fs_dist_download(fs_dist *d, fs_vec2f *v_rect, fs_rgb_uq32 *c_rect, float *p_rect, float *div_rect);
+/* device pointers of the CURRENT windows (they alternate from step to step like ino:255,286) */
+int fs_dist_device_fields(fs_dist *d, fs_vec2f **v, fs_rgb_uq32 **c, float **p, float **div);
+/* one loop() body; `drags` = the step's whole queue (HOST array; every rank passes all records) */
+int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags);
+/* FS_OK, FS_ERR_HALO_OVERRUN or FS_ERR_HALO_TIMEOUT since the last check; synchronises */
+int fs_dist_check(fs_dist *d);
 
 #ifdef __cplusplus
 }
