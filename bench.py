@@ -359,31 +359,68 @@ def bench_single(args, fb, synth, torch):
     sor_ms = s0.elapsed_time(s1) / reps
     peak, peak_src = measured_peaks()
     achieved = SOR_BYTES_PER_NODE_ITER * nodes * ITERS / (sor_ms * 1e-3) / 1e9
-    # `traffic`: ncu dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per LAUNCH
-    # (profiles/sor_traffic.json, from profiles/r01_ncu_sor_blocked_tma_final.json)
-    traffic = traffic_solve = None
+    # `traffic`: ncu dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per LAUNCH, from the
+    # ncu capture recorded in profiles/sor_traffic.json — used only if that capture was taken on the kernel
+    # configuration this run uses (strip shape + iterations per pass); otherwise null, never a stale constant
+    sor_t, sor_shape = ctx.get_option("sor_t"), ctx.get_option("sor_shape")
+    traffic = traffic_solve = traffic_src = None
     tpath = os.path.join(ROOT, "profiles", "sor_traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            traffic, traffic_solve = tj.get("dram_bytes_per_pass"), tj.get("dram_bytes_per_solve")
+            if tj.get("sor_t") == sor_t and tj.get("sor_shape") == sor_shape and tj.get("grid") == [n, n]:
+                traffic, traffic_solve = tj.get("dram_bytes_per_pass"), tj.get("dram_bytes_per_solve")
+                traffic_src = tj.get("source")
         except Exception:
             traffic = traffic_solve = None
     alg_launch = SOR_BYTES_PER_NODE_ITER * nodes * ITERS / max(sor_launches, 1)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src,
-        "kernel": "sor_blocked_tma_kernel: one launch = one pass of the SOR solve = up to 8 fused red-black "
-                  "iterations over the whole grid (fs_poisson_solve, K=50 => 7 launches)",
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+        "kernel": f"sor_blocked_tma_kernel (strip shape {sor_shape}): one launch = one pass of the SOR solve = up to "
+                  f"{sor_t} fused red-black iterations over the whole grid (fs_poisson_solve, K={ITERS} => "
+                  f"{sor_launches} launches)",
         "algorithmic_bytes_per_launch": alg_launch, "avg_launch_ms": sor_ms / max(sor_launches, 1),
         "algorithmic_bytes_per_solve": SOR_BYTES_PER_NODE_ITER * nodes * ITERS, "traffic_per_solve": traffic_solve,
         "note": "achieved = 12 B/node-iteration (SURVEY 8d) x nodes x iterations per launch / average launch time; "
-                "frac > 1 because temporal blocking moves ~1/8 of those bytes (see traffic)",
+                f"frac > 1 because temporal blocking moves ~1/{sor_t} of those bytes (see traffic); the kernel is "
+                "instruction-issue bound, not HBM bound (profiles/)",
         "ms": sor_ms, "launches_per_solve": sor_launches,
         "gnode_iters_per_s": nodes * ITERS / (sor_ms * 1e-3) / 1e9,
         "step_frac": (STEP_BYTES_PER_NODE * nodes / (ms * 1e-3) / 1e9) / peak,
         "sor_share_of_step": sor_ms / ms,
     }
+
+    # --- the advection kernels (north_star names them too): CUDA-event time of each, alone, on the same stream ---
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(reps):
+            fn()
+        a1.record(stream)
+        stream.synchronize()
+        return a0.elapsed_time(a1) / reps
+
+    with torch.cuda.stream(stream):
+        dv2 = torch.empty_like(dv)
+    adv = {}
+    for name, bpn, fn in (
+            ("advect velocity + drags + divergence (advect_div_tma_kernel, fused in fs_step)", 28.0,
+             lambda: ctx.advect_drags_divergence(dv2, dd, dv, drags[0], n, n, synth.DT, synth.DX)),
+            ("advect velocity (advect_tma_kernel<Vec2Payload>)", 16.0,
+             lambda: ctx.advect(dv2, dv, dv, n, n, synth.DT, True)),
+            ("advect dye (advect_tma_kernel<RgbPayload>)", 32.0,
+             lambda: ctx.advect(dc2, dc, dv, n, n, synth.DT, False))):
+        t_ms = timed(fn)
+        gbs = bpn * nodes / (t_ms * 1e-3) / 1e9
+        adv[name] = {"ms": t_ms, "algorithmic_bytes_per_node": bpn, "achieved": gbs, "unit": "GB/s", "frac": gbs / peak}
+    roofline_advect = {"bound": "hbm", "peak": peak, "peak_source": peak_src, "kernels": adv,
+                       "traffic": "profiles/ (ncu dram__bytes per launch of each kernel)",
+                       "note": "algorithmic bytes per node (SURVEY 8d): velocity 8 read + 8 written (+ 4 divergence "
+                               "written + the divergence kernel's 8 read saved = 28 for the fused kernel), dye 8 + 12 "
+                               "read + 12 written"}
 
     # --- e2e: the host-pointer drop-in fsh_step with pinned host buffers ---
     hv = torch.from_numpy(v0.copy()).pin_memory()
@@ -416,9 +453,9 @@ def bench_single(args, fb, synth, torch):
         "config": {"workload": f"single {n}x{n} grid, {ITERS} SOR iterations, velocity + dye advection",
                    "grid": [n, n], "sor_iters": ITERS, "drags_per_step": N_DRAGS,
                    "l2": "state (v 134 MB + dye 201 MB + p/div 134 MB) exceeds the 126 MB L2; no flush needed",
-                   "options": {k: ctx.get_option(k) for k in ("sor", "sor_t", "advect", "fuse")}},
+                   "options": {k: ctx.get_option(k) for k in ("sor", "sor_t", "sor_shape", "advect", "fuse")}},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "roofline_advect": roofline_advect, "cpu_baseline": cpu,
     }
 
 

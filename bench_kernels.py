@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--sor-sweep", default="", help="comma-separated SOR shapes: time poisson_solve for T = 4..8 each")
     ap.add_argument("--out", default="")
     ap.add_argument("--ensemble", type=int, default=0, help="batch size: bench the smem-resident ensemble kernel instead")
     ap.add_argument("--ens-shape", default="80x60")
@@ -85,7 +86,13 @@ def main():
         rec("step" + tag, ms, 80 + 12 * args.iters, {"mcell_steps_per_s": round(nodes / (ms * 1e-3) / 1e6, 1)})
 
     ctx.calculate_divergence(d, v, nx, ny, 1.0)
-    if args.sweep:
+    if args.sor_sweep:
+        for shape in (int(x) for x in args.sor_sweep.split(",")):
+            ctx.set_option("sor_shape", shape)
+            for t in (4, 5, 6, 7, 8):
+                ctx.set_option("sor_t", t)
+                run_sor(f"[blocked shape={shape} T={t}]")
+    elif args.sweep:
         for adv in (0, 1):
             ctx.set_option("advect", adv)
             run_ops(f"[advect={adv}]")
@@ -105,8 +112,8 @@ def main():
             for t in (2, 4, 6, 8):
                 ctx.set_option("sor_t", t)
                 run_sor(f"[blocked shape={shape} T={t}]")
-        ctx.set_option("sor_shape", 3)
-        ctx.set_option("sor_t", 8)
+        ctx.set_option("sor_shape", 7)
+        ctx.set_option("sor_t", 6)
         ctx.set_option("sor_one_launch", 0)
         for fuse in (0, 1, 2, 3):
             ctx.set_option("fuse", fuse)

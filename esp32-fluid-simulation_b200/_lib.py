@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
         "fs_apply_drags": ([vp, vp, I, I, I, vp], I),
         "fs_poisson_residual": ([C.POINTER(f), C.POINTER(C.c_double), vp, vp, I, I, f, vp], I),
         "fs_step": ([vp, vp, vp, I, I, I, f, f, I, f, vp, vp, vp], I),
+        "fs_advect_drags_divergence": ([vp, vp, vp, vp, I, I, I, f, f, vp], I),
         "fs_step_pingpong": ([vp, vp, vp, vp, I, I, I, f, f, I, f, vp, vp, vp], I),
         "fs_upscale4_rgb565": ([vp, vp, I, I, vp], I),
         "fs_ensemble_step": ([vp, vp, vp, vp, I, I, I, I, f, f, I, f, I, vp], I),

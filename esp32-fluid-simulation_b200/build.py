@@ -39,7 +39,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
         glob.glob(os.path.join(REPO_DIR, "include", "*.h")) + [os.path.abspath(__file__)]
     if force or _stale(LIB_PATH, deps):
         os.makedirs(LIB_DIR, exist_ok=True)
-        cmd = ["nvcc", *NVCC_FLAGS, "-o", LIB_PATH, *srcs]
+        cmd = ["nvcc", *NVCC_FLAGS, *os.environ.get("FS_NVCC_EXTRA", "").split(), "-o", LIB_PATH, *srcs]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True, cwd=REPO_DIR)

@@ -182,8 +182,8 @@ int fs_ctx_create(fs_ctx **out, int device, void *stream)
     ctx->num_sms = prop.multiProcessorCount;
     ctx->max_smem_optin = prop.sharedMemPerBlockOptin;
     ctx->opt_sor = 1;
-    ctx->opt_sor_t = 8;
-    ctx->opt_sor_shape = 3;
+    ctx->opt_sor_t = 6;
+    ctx->opt_sor_shape = 7;
     ctx->opt_sor_one_launch = 0;
     ctx->opt_halo_timeout_ms = 10000;
     ctx->opt_advect = 1;
@@ -363,6 +363,22 @@ int fs_apply_drags(fs_vec2f *v, const fs_drag *drags, int n, int dim_x, int dim_
     if (!v || n < 0 || (n > 0 && !drags) || bad_dims(dim_x, dim_y)) return FS_ERR_INVALID_ARG;
     DeviceGuard guard(ctx->device);
     return launch_apply_drags(mk(ctx), (float2 *)v, drags, n, geo_full(dim_x, dim_y));
+}
+
+int fs_advect_drags_divergence(fs_vec2f *v_out, float *div, const fs_vec2f *v_in, const fs_drag *drags, int n_drags,
+                               int dim_x, int dim_y, float dt, float dx, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!v_out || !div || !v_in || v_out == v_in || n_drags < 0 || (n_drags > 0 && !drags) || bad_dims(dim_x, dim_y))
+        return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    const Geo g = geo_full(dim_x, dim_y);
+    int e;
+    if (ctx->opt_advect == 1 && n_drags <= advect_div_max_drags() && advect_vec2f_tma_legal((const float2 *)v_in, g))
+        return launch_advect_div_tma(mk(ctx), (float2 *)v_out, (const float2 *)v_in, div, drags, n_drags, g, dt, dx);
+    if ((e = core_advect_vec2f(ctx, v_out, v_in, v_in, g, dt, 1, nullptr))) return e;
+    if (n_drags > 0 && (e = launch_apply_drags(mk(ctx), (float2 *)v_out, drags, n_drags, g))) return e;
+    return launch_divergence(mk(ctx), div, (const float2 *)v_out, g, dx);
 }
 
 int fs_step_pingpong(fs_vec2f *v, const fs_rgb_uq32 *c_in, fs_rgb_uq32 *c_out, const fs_drag *drags,

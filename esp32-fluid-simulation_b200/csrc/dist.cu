@@ -504,7 +504,7 @@ int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags)
                     push.signal[q] = flag_slot(n.base, -n.dx, -n.dy);
                 }
             }
-            const int shape = ctx->opt_sor_shape == 5 ? 5 : 3;
+            const int shape = (ctx->opt_sor_shape == 3 || ctx->opt_sor_shape == 5) ? ctx->opt_sor_shape : 7;
             if ((e = launch_sor_blocked_push(mk(ctx), bufs[k & 1], k ? bufs[(k - 1) & 1] : nullptr, div, gp, cfg.dx,
                                              cfg.omega, 0, 2 * t, shape, ctx->work_dev + k, push, ctx->opt_sor_grid_limit)))
                 return e > 0 ? e : FS_ERR_UNSUPPORTED;

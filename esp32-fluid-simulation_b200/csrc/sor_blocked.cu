@@ -56,6 +56,7 @@ struct BlockedArgs {
     int lax, lay;        // local coordinate of tile (0,0)'s first output node
     int tw_out, th_out;  // output tile size
     int vec_ok;          // rows are 16-byte aligned: float4 loads/stores allowed
+    int early_trigger;   // persistent kernels: let the next pass's CTAs take freed SMs early (PDL)
 };
 
 // One colour over a warp's strip.  Q = colour offset inside the strip: row r
@@ -123,6 +124,14 @@ __device__ __forceinline__ void strip_half_sweep(float (&p)[R][4], const float (
     }
 }
 
+// barrier over the NW compute warps only (named barrier 1): the persistent kernels run one more
+// warp — the producer — that must not take part in the sweeps' hand-offs
+template <int NW>
+__device__ __forceinline__ void compute_barrier()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+}
+
 // all H half-sweeps of one pass over a warp's strip, with the inter-warp row mailbox
 template <int R, int NW, int WALL>
 __device__ __forceinline__ void sweep_pass(float (&p)[R][4], const float (&dxd)[R][4], const BlockedArgs &a,
@@ -136,7 +145,7 @@ __device__ __forceinline__ void sweep_pass(float (&p)[R][4], const float (&dxd)[
         const int buf = s & 1;
         mail[buf][w][0][t] = make_float4(p[0][0], p[0][1], p[0][2], p[0][3]);
         mail[buf][w][1][t] = make_float4(p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3]);
-        __syncthreads();
+        compute_barrier<NW>();
         if (w > 0) {
             const float4 q = mail[buf][w - 1][1][t];
             dn[0] = q.x; dn[1] = q.y; dn[2] = q.z; dn[3] = q.w;
@@ -314,6 +323,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) sor_blocked_kernel(const Blocke
 // ---- loader 2: persistent CTAs, next tile prefetched into shared memory by TMA -----------------
 // The hardware zero-fills the parts of a region outside the window — exactly what loader 1 does by
 // hand.
+#ifdef FS_SOR_PROF
+// development aid (build with FS_NVCC_EXTRA=-DFS_SOR_PROF): per-CTA cycle sums of the tile phases
+__device__ unsigned long long g_sor_prof[1024][8];
+#define PROF_T(v) const long long v = clock64()
+#define PROF_ADD(slot, a, b) do { if (threadIdx.x == 0) g_sor_prof[blockIdx.x][slot] += (unsigned long long)((b) - (a)); } while (0)
+#else
+#define PROF_T(v)
+#define PROF_ADD(slot, a, b)
+#endif
+
 template <int R, int NW, int MINB, bool PUSH>
 __device__ __forceinline__ void sor_blocked_tma_body(const CUtensorMap &p_map, const CUtensorMap &d_map,
                                                      const BlockedArgs &a, int ntx, int nty, int *work_counter,
@@ -335,6 +354,8 @@ __device__ __forceinline__ void sor_blocked_tma_body(const CUtensorMap &p_map, c
     // thread 0: tiles are claimed dynamically (wall tiles cost more than interior ones) TWO ahead:
     // the ticket used for a prefetch was drawn one tile earlier, so the atomic's L2 round trip
     // (~1 us) is never waited for in front of the tile's first barrier.
+    // (A dedicated producer warp was built and measured in round 2: 17 warps cap the kernel at 120
+    // registers per thread, the sweeps spill, and the solve got 20-60 % SLOWER.)
     auto prefetch = [&](int idx) {
         if (idx < n_tiles) {
             int tx, ty;
@@ -350,21 +371,39 @@ __device__ __forceinline__ void sor_blocked_tma_body(const CUtensorMap &p_map, c
         mbar_init(&bar, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    // Programmatic dependent launch: this grid may have been scheduled while the previous pass was
-    // still draining; everything above overlapped with it, nothing below may (p_in is its output).
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Programmatic dependent launch, both directions.  (1) Let the NEXT pass's CTAs take this SM the
+    // moment this CTA exits: their prologue and their first d load then overlap this pass's tail.
+    if (a.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     int ahead = n_tiles;                       // thread 0 only: the ticket drawn one tile early
     if (threadIdx.x == 0) {
-        if constexpr (PUSH) {
-            if (push->n_wait > 0) wait_for_neighbours(*push);   // p_in's ghosts are the neighbours' previous pass
-        }
+        // (the tile counters of all passes were zeroed before the solve's first pass)
         const int first = atomicAdd(work_counter, 1);
         s_tile[0] = first;
-        prefetch(first);
+        if (first < n_tiles && has_p) {
+            // (2) this grid may have been scheduled while the previous pass is still draining: d does
+            // not depend on it — load it now; p_in is its output and must wait
+            int tx, ty;
+            tile_coords(first, ntx, nty, tx, ty);
+            const int x = a.lax + tx * a.tw_out - a.hpx, y = a.lay + ty * a.th_out - a.hpy;
+            mbar_expect_tx(&bar, tx_bytes);
+            tma_load_2d(sd, &d_map, x, y, &bar);
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            if constexpr (PUSH) {
+                if (push->n_wait > 0) wait_for_neighbours(*push);   // p_in's ghosts are the neighbours' previous pass
+            }
+            tma_load_2d(sp, &p_map, x, y, &bar);
+        } else {
+            asm volatile("griddepcontrol.wait;" ::: "memory");      // pass 1: d is the previous KERNEL's output
+            if constexpr (PUSH) {
+                if (push->n_wait > 0) wait_for_neighbours(*push);
+            }
+            prefetch(first);
+        }
         ahead = atomicAdd(work_counter, 1);
     }
     __syncthreads();
     uint32_t phase = 0;
+    PROF_T(t_begin);
     for (int it = 0;; it++) {
         const int idx = s_tile[it & 1];
         if (idx >= n_tiles) break;
@@ -375,7 +414,9 @@ __device__ __forceinline__ void sor_blocked_tma_body(const CUtensorMap &p_map, c
         const int lx0 = rlx0 + 4 * t, ly0 = rly0 + w * R;
         const int gi0 = g.ox + lx0, gj0 = g.oy + ly0;
 
+        PROF_T(t0);
         mbar_wait(&bar, phase);
+        PROF_T(t1);
         phase ^= 1;
         float p[R][4], dxd[R][4];
 #pragma unroll
@@ -393,13 +434,24 @@ __device__ __forceinline__ void sor_blocked_tma_body(const CUtensorMap &p_map, c
             }
         }
         __syncthreads();                       // every warp has drained the staging buffers
+        PROF_T(t2);
         if (threadIdx.x == 0) {
             s_tile[(it + 1) & 1] = ahead;      // visible after sweep_pass's first barrier
             prefetch(ahead);
             ahead = atomicAdd(work_counter, 1);   // consumed one tile later
         }
+        PROF_T(t3);
         sweep_region<R, NW>(p, dxd, a, mail, rlx0, rly0, gi0, gj0, a.n_half);
+        PROF_T(t4);
         store_tile<R, PUSH>(p, a, a.p_out, rlx0, rly0, lx0, ly0, push);
+        PROF_T(t5);
+        PROF_ADD(0, t0, t1);   // wait for the TMA
+        PROF_ADD(1, t1, t2);   // staging -> registers + barrier
+        PROF_ADD(2, t2, t3);   // issue the next prefetch
+        PROF_ADD(3, t3, t4);   // sweeps
+        PROF_ADD(4, t4, t5);   // store
+        PROF_ADD(5, 0, 1);     // tiles
+        PROF_ADD(6, t_begin, t5);
         if constexpr (PUSH) {
             if (push->n_peers > 0 && region_is_rim<R, NW>(g, *push, rlx0, rly0)) {
                 // publish: the CTA that completes the LAST rim tile tells every neighbour that this
@@ -416,6 +468,18 @@ __device__ __forceinline__ void sor_blocked_tma_body(const CUtensorMap &p_map, c
         }
     }
 }
+
+#ifdef FS_SOR_PROF
+extern "C" int fs_debug_sor_prof(unsigned long long *out, int reset)
+{
+    if (out) cudaMemcpyFromSymbol(out, g_sor_prof, sizeof(g_sor_prof));
+    if (reset) {
+        static unsigned long long zero[1024][8];
+        cudaMemcpyToSymbol(g_sor_prof, zero, sizeof(zero));
+    }
+    return 0;
+}
+#endif
 
 template <int R, int NW, int MINB>
 __global__ void __launch_bounds__(32 * NW, MINB)
@@ -635,6 +699,7 @@ static int launch_cfg_tma(const Launch &L, BlockedArgs &a, int *work_counter)
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    a.early_trigger = 1;
     e = cudaLaunchKernelEx(&cfg, sor_blocked_tma_kernel<R, NW, MINB>, p_map, d_map, a, ntx, nty, work_counter);
     ++*L.launches;
     return (int)e;
@@ -675,6 +740,8 @@ static int launch_cfg_push(const Launch &L, BlockedArgs &a, int *work_counter, S
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    // (not when several emulated ranks share the device: early CTAs would sit on SMs the other ranks need)
+    a.early_trigger = grid_limit > 0 ? 0 : 1;
     e = cudaLaunchKernelEx(&cfg, sor_blocked_push_kernel<R, NW, MINB>, p_map, d_map, a, ntx, nty, work_counter, push);
     ++*L.launches;
     return (int)e;
@@ -736,6 +803,7 @@ int launch_sor_solve(const Launch &L, float *p, float *scratch, const float *div
     a.k = make_sor_coef(dx, omega);
     a.first_parity = 0;
     a.vec_ok = 1;
+    a.early_trigger = 0;
     sa.passes = (iters + t_block - 1) / t_block;
     const int t_last = iters - (sa.passes - 1) * t_block;
     a.n_half = sa.passes > 1 ? 2 * t_block : 2 * t_last;   // tile geometry follows the regular pass
@@ -783,12 +851,16 @@ int launch_sor_blocked(const Launch &L, float *p_out, const float *p_in, const f
             return tma_ok ? launch_cfg_tma<10, 16, 1>(L, a, work_counter) : launch_cfg<12, 16, 1>(L, a);
         case 6:                                      // 128 x 192 region, 12 warps x 16 rows
             return tma_ok ? launch_cfg_tma<16, 12, 1>(L, a, work_counter) : launch_cfg<12, 16, 1>(L, a);
+        // (20 x 10 and 24 x 8 strips would hide more latency, but their row mailboxes push the CTA past
+        // 227 KB of shared memory next to the two staged regions)
+        case 7:                                      // 128 x 176 region, 16 warps x 11 rows
+            return tma_ok ? launch_cfg_tma<11, 16, 1>(L, a, work_counter) : launch_cfg<12, 16, 1>(L, a);
         default: return launch_cfg<12, 8, 2>(L, a);  // 128 x 96 region, two CTAs per SM
     }
 }
 
 // One blocked pass fused with its halo exchange (see SorPushArgs).  Needs the TMA loader: 16-byte
-// aligned rows and pointers (decomposed windows always are); shapes 3 and 5.
+// aligned rows and pointers (decomposed windows always are); shapes 3, 5 and 7 (default).
 int launch_sor_blocked_push(const Launch &L, float *p_out, const float *p_in, const float *div, const Geo &g,
                             float dx, float omega, int first_parity, int n_half, int shape, int *work_counter,
                             SorPushArgs &push, int grid_limit)
@@ -810,15 +882,20 @@ int launch_sor_blocked_push(const Launch &L, float *p_out, const float *p_in, co
         if ((q.sx0 | q.sx1 | q.dx | q.pitch) & 3 || (uintptr_t)q.base % 16) return (int)cudaErrorInvalidValue;
     }
     if (push.n_peers > 0 && ((g.x0 | g.x1) & 3)) return (int)cudaErrorInvalidValue;
-    return shape == 5 ? launch_cfg_push<10, 16, 1>(L, a, work_counter, push, grid_limit)
-                      : launch_cfg_push<12, 16, 1>(L, a, work_counter, push, grid_limit);
+    switch (shape) {
+        case 3: return launch_cfg_push<12, 16, 1>(L, a, work_counter, push, grid_limit);
+        case 5: return launch_cfg_push<10, 16, 1>(L, a, work_counter, push, grid_limit);
+        default: return launch_cfg_push<11, 16, 1>(L, a, work_counter, push, grid_limit);
+    }
 }
 
 int preload_sor_blocked_kernels()
 {
     FS_PRELOAD((sor_blocked_push_kernel<12, 16, 1>));
     FS_PRELOAD((sor_blocked_push_kernel<10, 16, 1>));
+    FS_PRELOAD((sor_blocked_push_kernel<11, 16, 1>));
     FS_PRELOAD((sor_blocked_tma_kernel<12, 16, 1>));
+    FS_PRELOAD((sor_blocked_tma_kernel<11, 16, 1>));
     FS_PRELOAD((sor_blocked_kernel<12, 16, 1>));
     return 0;
 }

@@ -202,6 +202,18 @@ class Context:
         check(fn(a_v, a_c, d.ctypes.data if nd else None, nd, dim_x, dim_y, dt, dx, iters, omega,
                  a_p or None, a_d or None, self._h), "step")
 
+    def advect_drags_divergence(self, v_out, div, v_in, drags, dim_x, dim_y, dt, dx):
+        """ino:253 + 264-269 + 274 in one pass (device tensors): v_out = forced advected velocity, div = its divergence."""
+        n = dim_x * dim_y
+        a_o, d0 = _ptr(v_out, "float32", 2 * n)
+        a_d, d1 = _ptr(div, "float32", n)
+        a_i, d2 = _ptr(v_in, "float32", 2 * n)
+        if not (d0 and d1 and d2):
+            raise ValueError("advect_drags_divergence: device tensors only")
+        d, nd = _drags(drags)
+        check(self._L.fs_advect_drags_divergence(a_o, a_d, a_i, d.ctypes.data if nd else None, nd, dim_x, dim_y, dt, dx,
+                                                 self._h), "fs_advect_drags_divergence")
+
     def step_pingpong(self, v, c_in, c_out, drags, dim_x, dim_y, dt, dx, iters, omega, p_out=None, div_out=None):
         """loop() body with the dye going c_in -> c_out (the caller swaps, ino:286); device tensors."""
         n = dim_x * dim_y

@@ -62,12 +62,12 @@ int  fs_ctx_destroy(fs_ctx *ctx);
 int  fs_ctx_synchronize(fs_ctx *ctx);
 /* Kernel-variant switches for A/B measurement (all variants are bit-identical):
  *   "sor"    : 0 = one half-sweep per launch, 1 = temporally blocked in registers + shared memory (default)
- *   "sor_t"  : full iterations fused per HBM round trip (1..8, default 8)
+ *   "sor_t"  : full iterations fused per HBM round trip (1..8, default 6)
  *   "sor_shape": CTA region and loader of the blocked solver: 0 = 128x96 nodes, 1 = 128x192, both
  *              loaded straight from global; 2 / 3 = the same regions with persistent CTAs whose
- *              next tile is prefetched by TMA (3 is the default; falls back to 1 when rows are
- *              not 16-byte multiples); 4 / 5 / 6 = TMA variants with 12x12, 16x10, 12x16
- *              (warps x rows per warp) strips
+ *              next tile is prefetched by TMA (fall back to 1 when rows are
+ *              not 16-byte multiples); 4 / 5 / 6 / 7 = TMA variants with 12x12, 16x10, 12x16,
+ *              16x11 (warps x rows per warp) strips; 7 is the default (spill-free, best wave count at 4096^2)
  *   "sor_one_launch": 1 = all passes of a solve run in ONE persistent launch with tile-level
  *              dependencies between passes (shapes 2, 3, 5); 0 (default) = one launch per pass.
  *              Measured: the dependency probes and release fences on the issuing thread cost more
@@ -127,6 +127,11 @@ int fs_apply_drags(fs_vec2f *v, const fs_drag *drags, int n, int dim_x, int dim_
 int fs_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags, int n_drags,
             int dim_x, int dim_y, float dt, float dx, int iters, float omega,
             float *p_out, float *div_out, fs_ctx *ctx);
+/* The first three operators of loop() in ONE pass over the grid (what fs_step runs): v_out = advect(v_in)
+ * with no-slip walls (ino:253), the drag records applied to v_out in queue order (ino:264-269), div =
+ * calculate_divergence(v_out) (ino:274).  v_out must not alias v_in; `drags` is a HOST array. */
+int fs_advect_drags_divergence(fs_vec2f *v_out, float *div, const fs_vec2f *v_in, const fs_drag *drags,
+                               int n_drags, int dim_x, int dim_y, float dt, float dx, fs_ctx *ctx);
 /* The same loop() body with the reference's dye pointer swap (ino:281-287) left to the caller:
  * the dye is read from c_in and the advected dye written to c_out (distinct buffers; the caller
  * alternates them from step to step like SWAP(c_temp, color_field)).  Saves fs_step's copy-back

@@ -95,8 +95,8 @@ def test_poisson_solve(ctx, oracle, sor_variant, shape, iters, omega, dx):
     assert_bit_equal(to_host(p), oracle.poisson_solve(d, dx, iters, omega), "pressure")
 
 
-@pytest.mark.parametrize("shape", [0, 1, 2, 3, 4, 5, 6],
-                         ids=["direct-96", "direct-192", "tma-96", "tma-192", "tma-144", "tma-160", "tma-192b"])
+@pytest.mark.parametrize("shape", [0, 1, 2, 3, 4, 5, 6, 7],
+                         ids=["direct-96", "direct-192", "tma-96", "tma-192", "tma-144", "tma-160", "tma-192b", "tma-176"])
 @pytest.mark.parametrize("one_launch", [1, 0], ids=["one-launch", "launch-per-pass"])
 @pytest.mark.parametrize("t_block", [1, 2, 3, 4, 6, 8])
 def test_poisson_solve_every_blocking_depth(ctx, oracle, t_block, shape, one_launch):
@@ -113,8 +113,8 @@ def test_poisson_solve_every_blocking_depth(ctx, oracle, t_block, shape, one_lau
             ctx.poisson_solve(p, to_dev(d), dim_x, dim_y, 1.0, iters, 1.96)
             assert_bit_equal(to_host(p), oracle.poisson_solve(d, 1.0, iters, 1.96), f"T={t_block}")
     finally:
-        ctx.set_option("sor_t", 8)
-        ctx.set_option("sor_shape", 3)
+        ctx.set_option("sor_t", 6)
+        ctx.set_option("sor_shape", 7)
         ctx.set_option("sor_one_launch", 0)
 
 
@@ -215,6 +215,19 @@ def test_step_matches_oracle(ctx, oracle, shape, iters, steps, fuse):
             assert_bit_equal(g, w, f"{name} after {steps} steps")
     finally:
         ctx.set_option("fuse", 1)
+
+
+@pytest.mark.parametrize("shape", [(61, 81), (256, 192), (1000, 333), (1024, 512)])
+def test_advect_drags_divergence(ctx, oracle, shape):
+    """The fused first half of loop() as its own entry point == advect, drags, divergence one after the other."""
+    dim_x, dim_y = shape
+    v, _ = rand_fields(21, dim_x, dim_y, 120.0)
+    dr = rand_drags(22, dim_x, dim_y, 40)
+    out, div = torch.empty(dim_y, dim_x, 2, device="cuda"), torch.empty(dim_y, dim_x, device="cuda")
+    ctx.advect_drags_divergence(out, div, to_dev(v), dr, dim_x, dim_y, DT, 1.0)
+    want = oracle.apply_drags(oracle.advect_vec2f(v, v, DT, True), dr)
+    assert_bit_equal(to_host(out), want, "forced velocity")
+    assert_bit_equal(to_host(div), oracle.calculate_divergence(want, 1.0), "divergence")
 
 
 def test_step_pingpong_equals_step(ctx, oracle):
