@@ -422,6 +422,29 @@ def bench_single(args, fb, synth, torch):
                                "written + the divergence kernel's 8 read saved = 28 for the fused kernel), dye 8 + 12 "
                                "read + 12 written"}
 
+    # --- BASELINE.json configs[1]: 65,536 independent 80x60 grids, one CTA per grid (fs_ensemble_step) ---
+    extra = {}
+    try:
+        eb, ex, ey, ek = 65536, 80, 60, 10
+        with torch.cuda.stream(stream):
+            g = torch.Generator(device="cuda").manual_seed(7)
+            ev = (torch.rand(eb, ey, ex, 2, device="cuda", generator=g) - 0.5) * 120.0
+            ec = torch.randint(0, 2 ** 31 - 1, (eb, ey, ex, 3), device="cuda", dtype=torch.int32, generator=g)
+        ens = {}
+        for n_steps in (1, 16):
+            t_ms = timed(lambda: ctx.ensemble_step(ev, ec, eb, ex, ey, synth.DT, synth.DX, ek, synth.OMEGA, n_steps), reps=3)
+            cells = eb * ex * ey * n_steps
+            ens[f"n_steps={n_steps}"] = {"ms": t_ms, "gcell_steps_per_s": cells / (t_ms * 1e-3) / 1e9,
+                                         "grid_steps_per_s": eb * n_steps / (t_ms * 1e-3),
+                                         "state_io_GBps": eb * ex * ey * 40 / (t_ms * 1e-3) / 1e9}
+        extra["ensemble"] = {"workload": f"{eb} independent {ex}x{ey} grids, K={ek}, one CTA per grid, state resident in "
+                                         "shared memory (BASELINE.json configs[1])", "results": ens,
+                             "bound": "instruction issue / shared memory (profiles/r02_ncu_ensemble*.json), not HBM: "
+                                      "state I/O is 40 B/node per CALL"}
+        del ev, ec
+    except Exception as e:  # noqa: BLE001 — never let an extra take the headline down
+        extra["ensemble"] = {"error": f"{type(e).__name__}: {e}"}
+
     # --- e2e: the host-pointer drop-in fsh_step with pinned host buffers ---
     hv = torch.from_numpy(v0.copy()).pin_memory()
     hc = torch.from_numpy(c0.view(np.int32).copy()).pin_memory()
@@ -455,7 +478,7 @@ def bench_single(args, fb, synth, torch):
                    "l2": "state (v 134 MB + dye 201 MB + p/div 134 MB) exceeds the 126 MB L2; no flush needed",
                    "options": {k: ctx.get_option(k) for k in ("sor", "sor_t", "sor_shape", "advect", "fuse")}},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_advect": roofline_advect, "cpu_baseline": cpu,
+        "roofline": roofline, "roofline_advect": roofline_advect, "cpu_baseline": cpu, "extra": extra,
     }
 
 

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--ensemble", type=int, default=0, help="batch size: bench the smem-resident ensemble kernel instead")
     ap.add_argument("--ens-shape", default="80x60")
+    ap.add_argument("--ens-variant", type=int, default=1)
     args = ap.parse_args()
     nx, ny = args.n, args.ny or args.n
     nodes = nx * ny
@@ -137,6 +138,7 @@ def bench_ensemble(args, ctx, stream, peak):
         c = torch.randint(0, 2 ** 31 - 1, (batch, dim_y, dim_x, 3), device="cuda", dtype=torch.int32, generator=g)
     stream.synchronize()
     rows = []
+    ctx.set_option("ensemble", args.ens_variant)
     for n_steps in (1, 4, 16):
         ms = timeit(stream, lambda: ctx.ensemble_step(v, c, batch, dim_x, dim_y, synth.DT, 1.0, iters, 1.96, n_steps),
                     reps=3, warm=1)

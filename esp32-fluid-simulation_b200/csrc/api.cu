@@ -186,6 +186,7 @@ int fs_ctx_create(fs_ctx **out, int device, void *stream)
     ctx->opt_sor_shape = 7;
     ctx->opt_sor_one_launch = 0;
     ctx->opt_halo_timeout_ms = 10000;
+    ctx->opt_ens = 0;
     ctx->opt_advect = 1;
     ctx->opt_fuse = 1;
     cudaError_t e = cudaMalloc(&ctx->status_dev, sizeof(int));
@@ -242,6 +243,7 @@ static int *opt_slot(fs_ctx *ctx, const char *name)
     if (!strcmp(name, "sor_one_launch")) return &ctx->opt_sor_one_launch;
     if (!strcmp(name, "halo_timeout_ms")) return &ctx->opt_halo_timeout_ms;
     if (!strcmp(name, "sor_grid_limit")) return &ctx->opt_sor_grid_limit;
+    if (!strcmp(name, "ensemble")) return &ctx->opt_ens;
     if (!strcmp(name, "advect")) return &ctx->opt_advect;
     if (!strcmp(name, "fuse")) return &ctx->opt_fuse;
     return nullptr;
@@ -450,9 +452,15 @@ int fs_ensemble_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags, const in
         FS_CUDA_TRY(cudaMemcpyAsync(d_counts, drag_counts, slots * sizeof(int), cudaMemcpyHostToDevice,
                                     ctx->stream));
     }
-    return launch_ensemble(mk(ctx), (float2 *)v, (uint32_t *)c, (const fs_drag *)d_drags,
+    void *d_scratch;
+    {
+        const int grid = ensemble_grid(batch, dim_x, dim_y, ctx->num_sms, ctx->opt_ens);
+        int e = ensure(ctx, S_ECTMP, ensemble_scratch_bytes(dim_x, dim_y, grid), &d_scratch);
+        if (e) return e;
+    }
+    return launch_ensemble(mk(ctx), (float2 *)v, (uint32_t *)c, (uint32_t *)d_scratch, (const fs_drag *)d_drags,
                            (const int *)d_counts, max_drags, batch, dim_x, dim_y, dt, dx, iters, omega,
-                           n_steps);
+                           n_steps, ctx->opt_ens);
 }
 
 // ---- host-pointer drop-ins --------------------------------------------------------

@@ -9,7 +9,7 @@
 using namespace fs;
 
 constexpr int WORK_SLOTS = 64;
-enum Scratch { S_VTMP = 0, S_CTMP, S_DIV, S_P, S_P2, S_HV, S_HV2, S_HC, S_HC2, S_HP, S_HD, S_HIMG, S_EDRAG, S_ECNT, S_SOLVE_FLAGS, S_COUNT };
+enum Scratch { S_VTMP = 0, S_CTMP, S_DIV, S_P, S_P2, S_HV, S_HV2, S_HC, S_HC2, S_HP, S_HD, S_HIMG, S_EDRAG, S_ECNT, S_ECTMP, S_SOLVE_FLAGS, S_COUNT };
 
 struct fs_ctx {
     int device;
@@ -30,6 +30,7 @@ struct fs_ctx {
     unsigned int solve_gen;     // generation stamp of the single-launch solve's completion flags
     int opt_sor_one_launch;
     int opt_halo_timeout_ms;
+    int opt_ens;                // ensemble kernel variant (CTA sizing), see fs_ctx_set_option
     int opt_sor_grid_limit;     // cap on the persistent SOR grid (0 = one CTA per SM): lets several emulated
                                 // ranks share one device without starving each other
     int opt_sor, opt_sor_t, opt_sor_shape, opt_advect, opt_fuse;

@@ -1,14 +1,20 @@
 // Batched ensemble of small grids (BASELINE.json configs[1]: 65,536 independent
 // 80x60-class sims): one CTA per grid, the WHOLE loop() body (ino:249-289) and
-// any number of consecutive steps run out of shared memory; HBM is touched only
-// to load the state once and to store it once per call (40 B/node).
+// any number of consecutive steps run with the velocity, divergence and pressure
+// resident in shared memory.
 //
-// Shared-memory plan for N = dim_x*dim_y nodes (40*N bytes; 61x81 -> 197.6 KB):
-//     A, B   : two velocity buffers (8N each).  advect reads A, writes B; A is
-//              then dead and is reused as d (4N) | p (4N) for the projection;
-//              the projected velocity ends up in B, and A/B swap roles.
-//     C1, C2 : two dye buffers (12N each), ping-pong for the dye advect.
-// (The reference's six separate arrays would need 48N = 237 KB > 227 KB.)
+// Shared-memory plan for N = dim_x*dim_y nodes (16*N bytes; 61x81 -> 79 KB, so TWO
+// grids are resident per SM and one grid's barriers overlap the other's work):
+//     A, B : two velocity buffers (8N each).  advect reads A, writes B; A is then
+//            dead and is reused as d (4N) | p (4N) for the projection; the
+//            projected velocity ends up in B, and A/B swap roles.
+//     dye  : NOT held in shared memory (24 of round 1's 40 B/node): the dye advect
+//            gathers it from global memory through L2 and writes the result back;
+//            between the steps of one call it ping-pongs between the caller's array
+//            and a per-CTA scratch slot that stays L2-resident.
+//     d, p : stored COLOUR-SEPARATED — node n lives at [colour(n)][n >> 1] — so the
+//            stride-2 red/black accesses of a half-sweep become unit-stride (round 1:
+//            43 % of the shared-memory wavefronts were bank conflicts).
 //
 // Work is organised by PAIRS of consecutive nodes (2q, 2q+1): a pair always holds
 // one node of each red/black colour, so in every half-sweep each thread updates
@@ -20,9 +26,7 @@
 
 namespace fs {
 
-constexpr int ENS_MAX_THREADS = 1024;
-constexpr int ENS_MAX_ROUNDS = 3;                                       // pairs per thread
-constexpr int ENS_MAX_NODES = 2 * ENS_MAX_THREADS * ENS_MAX_ROUNDS;     // also bounded by smem (40 B/node)
+constexpr int ENS_MAX_NODES = 6144;     // 2 nodes x threads x pairs per thread of every variant below
 
 template <class P>
 struct SmemFetch {
@@ -36,9 +40,26 @@ struct SmemFetch {
     }
 };
 
+// dye of one grid in global memory.  Plain (L1-cached) loads: every dye word is a corner of ~4
+// backtraces, and going to L2 for each of them cost 10x the grid's bytes in L2 traffic (measured:
+// the whole step 55 % slower).  The previous step's result was written by this very CTA — ordered
+// by the __syncthreads between the steps (CTA scope) — so only the read-only (ld.global.nc) path
+// must not be used.
+struct DyeFetch {
+    const uint32_t *base;
+    int dim_x;
+    __device__ __forceinline__ void operator()(int gi, int gj, uint32_t (&o)[3]) const
+    {
+        const uint32_t *q = base + (size_t)(gj * dim_x + gi) * 3;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) o[ch] = q[ch];
+    }
+};
+
 struct EnsArgs {
     float2 *v;
     uint32_t *c;
+    uint32_t *scratch;      // [gridDim.x][3N]: per-CTA dye ping-pong slot
     const fs_drag *drags;   // device: [n_steps][batch][max_drags]
     const int *counts;      // device: [n_steps][batch]
     int max_drags, batch, dim_x, dim_y, iters, n_steps;
@@ -46,18 +67,25 @@ struct EnsArgs {
     SorCoef k;
 };
 
-__global__ void __launch_bounds__(ENS_MAX_THREADS, 1) ensemble_kernel(const EnsArgs a)
+// ENS_MAX_THREADS x MINB = CTA size limit and CTAs per SM the kernel is compiled for; ENS_MAX_ROUNDS =
+// node pairs per thread
+// DYE_SMEM: both dye buffers live in shared memory too (40 B/node, one grid per SM) — faster than going
+// through L1/L2 for every corner while it fits; otherwise the dye is streamed (16 B/node).
+template <int ENS_MAX_THREADS, int MINB, int ENS_MAX_ROUNDS, bool DYE_SMEM>
+__global__ void __launch_bounds__(ENS_MAX_THREADS, MINB) ensemble_kernel(const EnsArgs a)
 {
     // the CTA is sized by the launcher so that the node pairs divide (almost) evenly over the threads:
     // every phase ends in a barrier, and idle threads in the last round were the top stall (ncu)
     const int ENS_THREADS = blockDim.x;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.dim_x * a.dim_y, dim_x = a.dim_x, dim_y = a.dim_y;
+    const int HQ = (N + 1) >> 1;                       // nodes per colour plane
     float2 *A = reinterpret_cast<float2 *>(smem_raw);
-    float2 *B = A + N;
-    uint32_t *C1 = reinterpret_cast<uint32_t *>(B + N);
-    uint32_t *C2 = C1 + 3 * (size_t)N;
+    float2 *B = A + N + 1;                             // + 8 bytes: the two colour planes of d and p need 4*(N+1) each
     const int tid = threadIdx.x;
+    // dye ping-pong: two shared-memory buffers, or the caller's array and this CTA's global scratch slot
+    uint32_t *C1 = DYE_SMEM ? reinterpret_cast<uint32_t *>(B + N) : nullptr;
+    uint32_t *C2 = DYE_SMEM ? C1 + 3 * (size_t)N : a.scratch + (size_t)blockIdx.x * N * 3;
 
     // this thread's pairs: node n0 = 2q at (i0, j0); n0+1 is the next node in index order
     int n0[ENS_MAX_ROUNDS], ij0[ENS_MAX_ROUNDS];
@@ -68,13 +96,40 @@ __global__ void __launch_bounds__(ENS_MAX_THREADS, 1) ensemble_kernel(const EnsA
         const int j = n / dim_x;
         ij0[r] = (j << 16) | (n - j * dim_x);
     }
+    // colour-separated address of node n: plane (i+j)&1, slot n>>1
+    auto cs = [&](int n, int colour) { return colour * HQ + (n >> 1); };
+    // SOR descriptors: for pair r and colour c, the node n of that colour: slot q = n>>1 (bits 0-12),
+    // b = n&1 (bit 13: the horizontal neighbours sit at slots q+b-1, q+b of the other plane), bo = b &
+    // (dim_x odd) (bit 14: the vertical neighbours at slots q+bo-hd0, q+bo+hu0), one bit per EXISTING
+    // neighbour (15 left, 16 right, 17 down, 18 up), and the index of neg_a_ii_inv[#neighbours] (19-20).
+    const int hu0 = dim_x >> 1, hd0 = (dim_x + 1) >> 1;
+    unsigned node_desc[ENS_MAX_ROUNDS][2];
+#pragma unroll
+    for (int r = 0; r < ENS_MAX_ROUNDS; r++) {
+        node_desc[r][0] = node_desc[r][1] = 0xffffffffu;
+        if (n0[r] < 0) continue;
+        int i = ij0[r] & 0xffff, j = ij0[r] >> 16;
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const int n = n0[r] + cc;
+            if (n < N) {
+                const unsigned hl = i > 0, hr = i < dim_x - 1, hd = j > 0, hu = j < dim_y - 1;
+                node_desc[r][(i + j) & 1] = (unsigned)(n >> 1) | ((unsigned)(n & 1) << 13) | ((unsigned)(n & dim_x & 1) << 14) |
+                                            (hl << 15) | (hr << 16) | (hd << 17) | (hu << 18) | ((4u - hl - hr - hd - hu) << 19);
+            }
+            if (++i == dim_x) { i = 0; j++; }
+        }
+    }
 
     for (int g = blockIdx.x; g < a.batch; g += gridDim.x) {
-        // ---- load the grid's state -------------------------------------------------------
+        // ---- load the grid's velocity -------------------------------------------------------
         const float2 *gv = a.v + (size_t)g * N;
-        const uint32_t *gc = a.c + (size_t)g * N * 3;
+        uint32_t *user_c = a.c + (size_t)g * N * 3;
         for (int n = tid; n < N; n += ENS_THREADS) A[n] = __ldg(gv + n);
-        for (int n = tid; n < 3 * N; n += ENS_THREADS) C1[n] = __ldg(gc + n);
+        if constexpr (DYE_SMEM)
+            for (int n = tid; n < 3 * N; n += ENS_THREADS) C1[n] = __ldg(user_c + n);
+        else
+            C1 = user_c;
         __syncthreads();
 
         for (int step = 0; step < a.n_steps; step++) {
@@ -100,19 +155,21 @@ __global__ void __launch_bounds__(ENS_MAX_THREADS, 1) ensemble_kernel(const EnsA
             }
             __syncthreads();
             // ---- drags (ino:264-269): in order, one thread ------------------------------------
-            if (a.max_drags > 0 && tid == 0) {
-                const size_t slot = (size_t)step * a.batch + g;
-                const int cnt = min(a.counts[slot], a.max_drags);
-                const fs_drag *dr = a.drags + slot * a.max_drags;
-                for (int q = 0; q < cnt; q++) {
-                    const fs_drag m = dr[q];
-                    if (m.cy < dim_x && m.cx < dim_y) B[m.cx * dim_x + m.cy] = make_float2(m.vy, m.vx);
+            if (a.max_drags > 0) {
+                if (tid == 0) {
+                    const size_t slot = (size_t)step * a.batch + g;
+                    const int cnt = min(a.counts[slot], a.max_drags);
+                    const fs_drag *dr = a.drags + slot * a.max_drags;
+                    for (int q = 0; q < cnt; q++) {
+                        const fs_drag m = dr[q];
+                        if (m.cy < dim_x && m.cx < dim_y) B[m.cx * dim_x + m.cy] = make_float2(m.vy, m.vx);
+                    }
                 }
+                __syncthreads();
             }
-            __syncthreads();
             // ---- divergence (ino:274) into d, zero p (poisson.cpp:117-119); A is dead now ------
-            float *d = reinterpret_cast<float *>(A);
-            float *p = d + N;
+            float *d = reinterpret_cast<float *>(A);    // [2][HQ] colour planes
+            float *p = d + 2 * HQ;                      // [2][HQ]
 #pragma unroll
             for (int r = 0; r < ENS_MAX_ROUNDS; r++) {
                 if (n0[r] < 0) continue;
@@ -135,38 +192,45 @@ __global__ void __launch_bounds__(ENS_MAX_THREADS, 1) ensemble_kernel(const EnsA
                             s = __fadd_rn(s, j < dim_y - 1 ? B[n + dim_x].y : -c0.y);
                         }
                         // store dx*d: the same product every iteration (poisson.cpp:88,109)
-                        d[n] = __fmul_rn(a.k.dx, __fmul_rn(s, a.two_dx_inv));
-                        p[n] = 0.0f;
+                        const int at = cs(n, (i + j) & 1);
+                        d[at] = __fmul_rn(a.k.dx, __fmul_rn(s, a.two_dx_inv));
+                        p[at] = 0.0f;
                     }
                     if (++i == dim_x) { i = 0; j++; }
                 }
             }
             __syncthreads();
             // ---- red-black SOR (ino:275): colour 0 = (i+j) even first ---------------------------
-            for (int hs = 0; hs < 2 * a.iters; hs++) {
-                const int parity = hs & 1;
+            // Every thread updates the colour-`parity` node of each of its pairs; everything about
+            // that node that does not change between half-sweeps (slot, which neighbours exist, the
+            // Gauss-Seidel coefficient) was packed into one register per (pair, colour) before the
+            // loop.  ONE branch-free path for interior and wall nodes: a missing neighbour enters the
+            // interior sum ((L+R)+D)+U as +0.0f, which is bit-identical to pois_gs_safe's running sum
+            // (sor.cuh: sor_update_coef) — a warp of 64 consecutive nodes nearly always holds a wall
+            // node, so the two-path version executed both paths for almost every warp (ncu: the SOR
+            // phase was 64 % of 1,257 thread-instructions per node-step).
+            for (int hs = 0; hs < 2 * a.iters; hs += 2) {
 #pragma unroll
-                for (int r = 0; r < ENS_MAX_ROUNDS; r++) {
-                    if (n0[r] < 0) continue;
-                    int i = ij0[r] & 0xffff, j = ij0[r] >> 16;
-                    int n = n0[r];
-                    if (((i + j) & 1) != parity) {      // the pair's other node has this colour
-                        n++;
-                        if (++i == dim_x) { i = 0; j++; }
+                for (int parity = 0; parity < 2; parity++) {
+                    float *pm = p + parity * HQ;               // the plane being updated
+                    const float *po = p + (parity ^ 1) * HQ;   // its neighbours' plane
+                    const float *dm = d + parity * HQ;
+#pragma unroll
+                    for (int r = 0; r < ENS_MAX_ROUNDS; r++) {
+                        const unsigned desc = node_desc[r][parity];
+                        if (desc == 0xffffffffu) continue;     // no such node
+                        const int q = desc & 0x1fff;
+                        const float *ctr = po + q + ((desc >> 13) & 1);    // left neighbour at ctr[-1], right at ctr[0]
+                        const float *ver = po + q + ((desc >> 14) & 1);    // down at ver[-hd0], up at ver[hu0]
+                        // unconditional loads (always inside the CTA's shared memory), then selects
+                        const float l = (desc & (1u << 15)) ? ctr[-1] : 0.0f, rr = (desc & (1u << 16)) ? ctr[0] : 0.0f;
+                        const float dn = (desc & (1u << 17)) ? ver[-hd0] : 0.0f, up = (desc & (1u << 18)) ? ver[hu0] : 0.0f;
+                        const unsigned ci = desc >> 19;        // 0: 4 neighbours, 1: 3, 2: 2
+                        const float coef = ci == 0 ? a.k.neg_quarter : ci == 1 ? a.k.neg_third : a.k.neg_half;
+                        pm[q] = sor_update_coef(pm[q], l, rr, dn, up, dm[q], coef, a.k);
                     }
-                    if (n >= N) continue;
-                    const bool hl = i > 0, hr = i < dim_x - 1, hd = j > 0, hu = j < dim_y - 1;
-                    const float pc = p[n];
-                    float out;
-                    if (hl && hr && hd && hu)
-                        out = sor_update_interior(pc, p[n - 1], p[n + 1], p[n - dim_x], p[n + dim_x], d[n], a.k);
-                    else
-                        out = sor_update_wall(pc, hl ? p[n - 1] : 0.f, hr ? p[n + 1] : 0.f,
-                                              hd ? p[n - dim_x] : 0.f, hu ? p[n + dim_x] : 0.f, hl, hr,
-                                              hd, hu, d[n], a.k);
-                    p[n] = out;
+                    __syncthreads();
                 }
-                __syncthreads();
             }
             // ---- subtract gradient (ino:276), in place on B --------------------------------------
 #pragma unroll
@@ -177,9 +241,11 @@ __global__ void __launch_bounds__(ENS_MAX_THREADS, 1) ensemble_kernel(const EnsA
                 for (int cc = 0; cc < 2; cc++) {
                     const int n = n0[r] + cc;
                     if (n < N) {
-                        const float pc = p[n];
-                        const float pl = i > 0 ? p[n - 1] : pc, pr = i < dim_x - 1 ? p[n + 1] : pc;
-                        const float pd = j > 0 ? p[n - dim_x] : pc, pu = j < dim_y - 1 ? p[n + dim_x] : pc;
+                        const int col = (i + j) & 1;
+                        const float *po = p + (col ^ 1) * HQ;
+                        const float pc = p[cs(n, col)];
+                        const float pl = i > 0 ? po[(n - 1) >> 1] : pc, pr = i < dim_x - 1 ? po[(n + 1) >> 1] : pc;
+                        const float pd = j > 0 ? po[(n - dim_x) >> 1] : pc, pu = j < dim_y - 1 ? po[(n + dim_x) >> 1] : pc;
                         float2 c0 = B[n];
                         c0.x = __fsub_rn(c0.x, __fmul_rn(__fsub_rn(pr, pl), a.two_dx_inv));
                         c0.y = __fsub_rn(c0.y, __fmul_rn(__fsub_rn(pu, pd), a.two_dx_inv));
@@ -189,9 +255,9 @@ __global__ void __launch_bounds__(ENS_MAX_THREADS, 1) ensemble_kernel(const EnsA
                 }
             }
             __syncthreads();
-            // ---- advect dye, free-slip sampling (ino:282): C1 -> C2 with the projected velocity -----
+            // ---- advect dye, free-slip sampling (ino:282) with the projected velocity: C1 -> C2 ---------
             {
-                SmemFetch<RgbPayload> fetch{C1, dim_x};
+                DyeFetch fetch{C1, dim_x};
 #pragma unroll
                 for (int r = 0; r < ENS_MAX_ROUNDS; r++) {
                     if (n0[r] < 0) continue;
@@ -212,52 +278,90 @@ __global__ void __launch_bounds__(ENS_MAX_THREADS, 1) ensemble_kernel(const EnsA
                     }
                 }
             }
-            __syncthreads();
+            __syncthreads();                // (CTA-scope ordering of the dye stores before the next step's reads)
             // pointer swaps of ino:255 and ino:286
-            float2 *tv = A; A = B; B = tv;
             uint32_t *tc = C1; C1 = C2; C2 = tc;
+            float2 *tv = A; A = B; B = tv;
         }
 
         // ---- store the grid's state ----------------------------------------------------------
         float2 *ov = a.v + (size_t)g * N;
-        uint32_t *oc = a.c + (size_t)g * N * 3;
         for (int n = tid; n < N; n += ENS_THREADS) ov[n] = A[n];
-        for (int n = tid; n < 3 * N; n += ENS_THREADS) oc[n] = C1[n];
+        if (C1 != user_c)                   // the final dye sits in shared memory / in the scratch slot
+            for (int n = tid; n < 3 * N; n += ENS_THREADS) user_c[n] = C1[n];
         __syncthreads();
+        if constexpr (!DYE_SMEM) C2 = a.scratch + (size_t)blockIdx.x * N * 3;   // next grid: C1 = its own array again
     }
 }
 
-size_t ensemble_smem_bytes(int dim_x, int dim_y) { return (size_t)40 * dim_x * dim_y; }
+size_t ensemble_scratch_bytes(int dim_x, int dim_y, int grid) { return (size_t)grid * dim_x * dim_y * 12; }
+
+size_t ensemble_smem_bytes(int dim_x, int dim_y, bool dye_smem)
+{
+    return (size_t)(dye_smem ? 40 : 16) * dim_x * dim_y + 16;
+}
+
+// variant 0 (default): dye in shared memory while 40 B/node fit one CTA, else streamed; 1/2/3: streamed dye, two
+// CTAs per SM; 4: streamed dye, one CTA per SM
+static bool ens_dye_smem(int dim_x, int dim_y, int variant)
+{
+    return variant == 0 && ensemble_smem_bytes(dim_x, dim_y, true) <= 227 * 1024 &&
+           (dim_x * dim_y + 1) / 2 <= 1024 * 3;
+}
+
 
 bool ensemble_supported(int dim_x, int dim_y, size_t max_smem_optin)
 {
     const long long n = (long long)dim_x * dim_y;
-    return dim_x < 65536 && dim_y < 32768 && n <= ENS_MAX_NODES && (size_t)(40 * n) <= max_smem_optin;
+    return dim_x < 65536 && dim_y < 32768 && n <= ENS_MAX_NODES && (size_t)(16 * n + 16) <= max_smem_optin;
 }
 
-int launch_ensemble(const Launch &L, float2 *v, uint32_t *c, const fs_drag *drags_dev,
+int ensemble_grid(int batch, int dim_x, int dim_y, int num_sms, int variant)
+{
+    // persistent CTAs walking the batch: one per SM, or two when the variant streams the dye and 2 x 16N bytes fit
+    int per_sm = 1;
+    if (!ens_dye_smem(dim_x, dim_y, variant) && variant != 4 && ensemble_smem_bytes(dim_x, dim_y, false) * 2 + 2048 <= 227 * 1024)
+        per_sm = 2;
+    return batch < per_sm * num_sms ? batch : per_sm * num_sms;
+}
+
+template <int MAXT, int MINB, int ROUNDS, bool DYE_SMEM>
+static int launch_ens(const Launch &L, const EnsArgs &a, int grid, int threads_override)
+{
+    const size_t smem = ensemble_smem_bytes(a.dim_x, a.dim_y, DYE_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(ensemble_kernel<MAXT, MINB, ROUNDS, DYE_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    // threads: ROUNDS pairs per thread, rounded up to whole warps
+    const int pairs = (a.dim_x * a.dim_y + 1) / 2;
+    int threads = ((pairs + ROUNDS - 1) / ROUNDS + 31) / 32 * 32;
+    if (threads_override > 0 && threads_override * ROUNDS >= pairs) threads = threads_override;
+    if (threads < 128) threads = 128;
+    if (threads > MAXT || threads * ROUNDS < pairs) return (int)cudaErrorInvalidValue;
+    ensemble_kernel<MAXT, MINB, ROUNDS, DYE_SMEM><<<grid, threads, smem, L.stream>>>(a);
+    ++*L.launches;
+    return (int)cudaGetLastError();
+}
+
+int launch_ensemble(const Launch &L, float2 *v, uint32_t *c, uint32_t *scratch, const fs_drag *drags_dev,
                     const int *counts_dev, int max_drags, int batch, int dim_x, int dim_y, float dt,
-                    float dx, int iters, float omega, int n_steps)
+                    float dx, int iters, float omega, int n_steps, int variant)
 {
     if (batch <= 0 || n_steps <= 0) return 0;
     EnsArgs a;
-    a.v = v; a.c = c; a.drags = drags_dev; a.counts = counts_dev;
+    a.v = v; a.c = c; a.scratch = scratch; a.drags = drags_dev; a.counts = counts_dev;
     a.max_drags = max_drags; a.batch = batch; a.dim_x = dim_x; a.dim_y = dim_y;
     a.iters = iters; a.n_steps = n_steps; a.dt = dt;
     a.two_dx_inv = 1.0f / (2.0f * dx);
     a.k = make_sor_coef(dx, omega);
-    const size_t smem = ensemble_smem_bytes(dim_x, dim_y);
-    cudaError_t e = cudaFuncSetAttribute(ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    const int grid = batch < L.num_sms ? batch : L.num_sms;   // persistent: one CTA per SM walks the batch
-    // threads: ENS_MAX_ROUNDS pairs per thread, rounded up to whole warps (80x60 -> 800, 61x81 -> 832)
-    const int pairs = (dim_x * dim_y + 1) / 2;
-    int threads = ((pairs + ENS_MAX_ROUNDS - 1) / ENS_MAX_ROUNDS + 31) / 32 * 32;
-    if (threads < 128) threads = 128;
-    if (threads > ENS_MAX_THREADS) threads = ENS_MAX_THREADS;
-    ensemble_kernel<<<grid, threads, smem, L.stream>>>(a);
-    ++*L.launches;
-    return (int)cudaGetLastError();
+    const int grid = ensemble_grid(batch, dim_x, dim_y, L.num_sms, variant);
+    if (ens_dye_smem(dim_x, dim_y, variant)) return launch_ens<1024, 1, 3, true>(L, a, grid, 0);   // everything resident
+    switch (variant) {
+        case 1: return launch_ens<512, 2, 6, false>(L, a, grid, 0);       // two grids per SM, 6 pairs per thread
+        case 2: return launch_ens<512, 2, 6, false>(L, a, grid, 512);     // two grids per SM, 16 warps each
+        case 3: return launch_ens<512, 2, 6, false>(L, a, grid, 384);     // two grids per SM, 12 warps each
+        case 4: return launch_ens<1024, 1, 3, false>(L, a, grid, 0);      // one grid per SM, dye streamed
+        default: return launch_ens<512, 2, 6, false>(L, a, grid, 0);      // (too large for 40 B/node)
+    }
 }
 
 }  // namespace fs

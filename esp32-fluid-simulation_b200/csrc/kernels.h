@@ -88,11 +88,13 @@ int launch_sor_blocked_push(const Launch &L, float *p_out, const float *p_in, co
                             SorPushArgs &push, int grid_limit);
 
 // ensemble.cu — whole loop() body per grid, resident in shared memory
-size_t ensemble_smem_bytes(int dim_x, int dim_y);
+size_t ensemble_smem_bytes(int dim_x, int dim_y, bool dye_smem);
 bool ensemble_supported(int dim_x, int dim_y, size_t max_smem_optin);
-int launch_ensemble(const Launch &L, float2 *v, uint32_t *c, const fs_drag *drags_dev,
+int ensemble_grid(int batch, int dim_x, int dim_y, int num_sms, int variant);
+size_t ensemble_scratch_bytes(int dim_x, int dim_y, int grid);   // per-CTA dye ping-pong slots
+int launch_ensemble(const Launch &L, float2 *v, uint32_t *c, uint32_t *scratch, const fs_drag *drags_dev,
                     const int *counts_dev, int max_drags, int batch, int dim_x, int dim_y, float dt,
-                    float dx, int iters, float omega, int n_steps);
+                    float dx, int iters, float omega, int n_steps, int variant);
 
 // the whole solve in ONE persistent launch with tile-level dependencies between passes; returns -1
 // when not eligible (caller falls back to one launch per pass)

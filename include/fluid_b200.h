@@ -145,11 +145,12 @@ int fs_step_pingpong(fs_vec2f *v, const fs_rgb_uq32 *c_in, fs_rgb_uq32 *c_out, c
 int fs_upscale4_rgb565(uint16_t *out, const fs_rgb_uq32 *c, int dim_x, int dim_y,
                        fs_ctx *ctx);
 /* `batch` independent grids, `n_steps` consecutive loop() bodies each, one CTA per
- * grid with the grid resident in shared memory for the whole call (BASELINE.json
- * configs[1]).  v, c hold the grids back to back.  drags: HOST array laid out
- * [n_steps][batch][max_drags], drag_counts: HOST array [n_steps][batch] (both may
- * be NULL with max_drags = 0).  Needs 40*dim_x*dim_y bytes of shared memory:
- * FS_ERR_UNSUPPORTED beyond ~5,700 nodes (use fs_step per grid there). */
+ * grid with the grid's velocity / divergence / pressure resident in shared memory for the
+ * whole call and its dye streamed through L2 (BASELINE.json configs[1]).  v, c hold the
+ * grids back to back.  drags: HOST array laid out [n_steps][batch][max_drags],
+ * drag_counts: HOST array [n_steps][batch] (both may be NULL with max_drags = 0).
+ * Needs 16*dim_x*dim_y bytes of shared memory (two grids per SM up to ~7,000 nodes):
+ * FS_ERR_UNSUPPORTED beyond 6,144 nodes (use fs_step per grid there). */
 int fs_ensemble_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags,
                      const int *drag_counts, int max_drags, int batch, int dim_x,
                      int dim_y, float dt, float dx, int iters, float omega,
