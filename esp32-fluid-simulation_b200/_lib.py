@@ -85,6 +85,9 @@ def lib() -> C.CDLL:
         "fs_step_pingpong": ([vp, vp, vp, vp, I, I, I, f, f, I, f, vp, vp, vp], I),
         "fs_upscale4_rgb565": ([vp, vp, I, I, vp], I),
         "fs_ensemble_step": ([vp, vp, vp, vp, I, I, I, I, f, f, I, f, I, vp], I),
+        "fs_ensemble_step_dev": ([vp, vp, vp, vp, I, I, I, I, f, f, I, f, I, vp], I),
+        "fs_init_color_wheel": ([vp, vp, I, I, I, vp], I),
+        "fs_touch_to_drags": ([vp, vp, vp, I, I, I, I, I, vp, vp], I),
         "fsh_advect_vec2f": ([vp, vp, vp, I, I, f, I, vp], I),
         "fsh_advect_rgb_uq32": ([vp, vp, vp, I, I, f, I, vp], I),
         "fsh_calculate_divergence": ([vp, vp, I, I, f, vp], I),

@@ -463,6 +463,49 @@ int fs_ensemble_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags, const in
                            n_steps, ctx->opt_ens);
 }
 
+int fs_ensemble_step_dev(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags_dev, const int *counts_dev, int max_drags,
+                         int batch, int dim_x, int dim_y, float dt, float dx, int iters, float omega, int n_steps,
+                         fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!v || !c || batch < 0 || n_steps < 0 || iters < 0 || max_drags < 0 || bad_dims(dim_x, dim_y) ||
+        (max_drags > 0 && (!drags_dev || !counts_dev)))
+        return FS_ERR_INVALID_ARG;
+    if (!ensemble_supported(dim_x, dim_y, ctx->max_smem_optin)) return FS_ERR_UNSUPPORTED;
+    if (batch == 0 || n_steps == 0) return FS_OK;
+    DeviceGuard guard(ctx->device);
+    void *d_scratch;
+    const int grid = ensemble_grid(batch, dim_x, dim_y, ctx->num_sms, ctx->opt_ens);
+    int e = ensure(ctx, S_ECTMP, ensemble_scratch_bytes(dim_x, dim_y, grid), &d_scratch);
+    if (e) return e;
+    return launch_ensemble(mk(ctx), (float2 *)v, (uint32_t *)c, (uint32_t *)d_scratch, drags_dev, counts_dev, max_drags,
+                           batch, dim_x, dim_y, dt, dx, iters, omega, n_steps, ctx->opt_ens);
+}
+
+int fs_init_color_wheel(fs_vec2f *v, fs_rgb_uq32 *c, int batch, int dim_x, int dim_y, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!v || !c || batch < 0 || bad_dims(dim_x, dim_y) || (long long)batch * dim_x * dim_y > 0x7fffffffLL)
+        return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return launch_init_color_wheel(mk(ctx), (float2 *)v, (uint32_t *)c, batch, dim_x, dim_y);
+}
+
+int fs_touch_to_drags(fs_drag *drags_out, int *counts_out, const int *samples, int n_samples, int batch, int max_drags,
+                      int n_rows, int n_cols, const fs_touch_cal *cal, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!drags_out || !counts_out || !samples || n_samples < 0 || batch < 0 || max_drags < 1 || n_rows < 1 || n_cols < 1)
+        return FS_ERR_INVALID_ARG;
+    const fs_touch_cal def = {200, 3700, 240, 3800, 10};      // ino:17-21
+    if (!cal) cal = &def;
+    if (cal->polling_ms <= 0) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    const int c4[4] = {cal->min_x, cal->max_x, cal->min_y, cal->max_y};
+    return launch_touch_to_drags(mk(ctx), drags_out, counts_out, samples, n_samples, batch, max_drags, n_rows, n_cols, c4,
+                                 cal->polling_ms);
+}
+
 // ---- host-pointer drop-ins --------------------------------------------------------
 
 #define H2D(dst, src, bytes) FS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream))

@@ -122,6 +122,11 @@ struct HaloArgs {
 };
 int launch_halo_exchange(const Launch &L, HaloArgs &a, unsigned int *done_counter, int *status);
 
+// inputs.cu — setup() ino:196-241 and touch_routine() ino:63-96 on the device
+int launch_init_color_wheel(const Launch &L, float2 *v, uint32_t *c, int batch, int dim_x, int dim_y);
+int launch_touch_to_drags(const Launch &L, fs_drag *drags, int *counts, const int *samples, int n_samples, int batch,
+                          int max_drags, int n_rows, int n_cols, const int cal[4], int polling_ms);
+
 // Load every kernel a decomposed step can launch (see FS_PRELOAD below): returns a cudaError_t.
 int preload_advect_kernels();
 int preload_advect_tma_kernels();

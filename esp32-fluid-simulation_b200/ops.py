@@ -252,6 +252,30 @@ class Context:
         check(self._L.fs_ensemble_step(a_v, a_c, dptr, cptr, max_drags, batch, dim_x, dim_y, dt, dx,
                                        iters, omega, n_steps, self._h), "fs_ensemble_step")
 
+    def ensemble_step_dev(self, v, c, drags_dev, counts_dev, max_drags, batch, dim_x, dim_y, dt, dx, iters, omega,
+                          n_steps=1):
+        """fs_ensemble_step with device-resident drag records (int32 view of [n_steps, batch, max_drags, 3] words)."""
+        n = batch * dim_x * dim_y
+        a_v, _ = _ptr(v, "float32", 2 * n)
+        a_c, _ = _ptr(c, "uint32", 3 * n)
+        check(self._L.fs_ensemble_step_dev(a_v, a_c, drags_dev.data_ptr(), counts_dev.data_ptr(), max_drags, batch, dim_x,
+                                           dim_y, dt, dx, iters, omega, n_steps, self._h), "fs_ensemble_step_dev")
+
+    def init_color_wheel(self, v, c, batch, dim_x, dim_y):
+        """setup(), ino:196-241, on the device (device tensors, `batch` grids back to back)."""
+        n = batch * dim_x * dim_y
+        a_v, d0 = _ptr(v, "float32", 2 * n)
+        a_c, d1 = _ptr(c, "uint32", 3 * n)
+        if not (d0 and d1):
+            raise ValueError("init_color_wheel: device tensors only")
+        check(self._L.fs_init_color_wheel(a_v, a_c, batch, dim_x, dim_y, self._h), "fs_init_color_wheel")
+
+    def touch_to_drags(self, drags_out, counts_out, samples, n_samples, batch, max_drags, n_rows, n_cols):
+        """touch_routine(), ino:63-96, on the device.  drags_out: int32 device tensor [batch, max_drags, 3] (12-byte
+        records), counts_out: int32 [batch], samples: int32 [batch, n_samples, 3]."""
+        check(self._L.fs_touch_to_drags(drags_out.data_ptr(), counts_out.data_ptr(), samples.data_ptr(), n_samples, batch,
+                                        max_drags, n_rows, n_cols, None, self._h), "fs_touch_to_drags")
+
     # --- decomposed grids ----------------------------------------------------------------
     def tile_advect(self, next_p, p, vel, tile: Tile, dt, no_slip):
         kind = _payload(p)

@@ -156,6 +156,26 @@ int fs_ensemble_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags,
                      int dim_y, float dt, float dx, int iters, float omega,
                      int n_steps, fs_ctx *ctx);
 
+/* fs_ensemble_step with the drag records already ON THE DEVICE ([n_steps][batch][max_drags] records,
+ * [n_steps][batch] counts) — e.g. written by fs_touch_to_drags — so an ensemble is driven without host
+ * round trips. */
+int fs_ensemble_step_dev(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags_dev, const int *counts_dev,
+                         int max_drags, int batch, int dim_x, int dim_y, float dt, float dx, int iters,
+                         float omega, int n_steps, fs_ctx *ctx);
+/* setup(), ino:196-241, on the device: zero velocity, the three-sector colour wheel (atan2f of the
+ * node's offset from the centre against +-PI/3) and the two IN-PLACE 1-2-1 smoothing passes (first
+ * along j, then along i; each reads its already-smoothed predecessor).  Every one of the `batch`
+ * grids (laid out back to back) receives the same initial condition. */
+int fs_init_color_wheel(fs_vec2f *v, fs_rgb_uq32 *c, int batch, int dim_x, int dim_y, fs_ctx *ctx);
+/* touch_routine(), ino:63-96, on the device.  samples: [batch][n_samples][3] int32 = {touched, raw x,
+ * raw y}, one per polling period; every touched sample whose predecessor was touched becomes a drag
+ * record {coords = map() of the raw reading onto [0,n_cols] x [0,n_rows] (ino:77-78), velocity =
+ * delta * 1000.f / polling_ms (ino:82-83)}, in order, at most max_drags per grid (the sketch's queue
+ * holds 10 and drops the rest, ino:49,85).  cal == NULL: the sketch's calibration (ino:17-21). */
+typedef struct fs_touch_cal { int min_x, max_x, min_y, max_y, polling_ms; } fs_touch_cal;
+int fs_touch_to_drags(fs_drag *drags_out, int *counts_out, const int *samples, int n_samples, int batch,
+                      int max_drags, int n_rows, int n_cols, const fs_touch_cal *cal, fs_ctx *ctx);
+
 /* ---- the same operators over HOST pointers (reference drop-ins) ------------- */
 int fsh_advect_vec2f(fs_vec2f *next_p, const fs_vec2f *p, const fs_vec2f *vel,
                      int dim_x, int dim_y, float dt, int no_slip, fs_ctx *ctx);

@@ -407,3 +407,73 @@ def test_poisson_residual(ctx, oracle, shape):
         assert np.float32(m) == np.abs(r).max()
         assert abs(l2 - np.sqrt((r.astype(np.float64) ** 2).sum())) <= 1e-6 * max(l2, 1e-30)
         assert np.isfinite(l2)
+
+
+# ---- the sketch's own initial condition and input path on the device ------------------
+
+@pytest.mark.parametrize("shape,batch", [((61, 81), 1), ((80, 60), 3), ((5, 4), 2), ((2, 2), 1), ((16, 9), 1), ((512, 300), 1),
+                                         ((1024, 768), 1)])
+def test_init_color_wheel_on_device(ctx, oracle, shape, batch):
+    """fs_init_color_wheel == setup() of the sketch (ino:196-241; the compiled sketch when oracle/_ref travelled)."""
+    dim_x, dim_y = shape
+    v = torch.full((batch, dim_y, dim_x, 2), 7.0, device="cuda")
+    c = torch.full((batch, dim_y, dim_x, 3), 7, dtype=torch.int32, device="cuda")
+    ctx.init_color_wheel(v, c, batch, dim_x, dim_y)
+    ov, oc = oracle.init_color_wheel(dim_x, dim_y)
+    for b in range(batch):
+        assert_bit_equal(to_host(v[b]), ov, f"velocity, grid {b}")
+        assert_bit_equal(to_host(c[b], np.uint32), oc, f"dye, grid {b}")
+
+
+def test_touch_to_drags_on_device(ctx, oracle):
+    """fs_touch_to_drags == touch_routine() of the sketch (ino:63-96), incl. the queue's depth-10 drop."""
+    from esp32_fluid_simulation_b200 import synth
+    rng = np.random.default_rng(11)
+    batch, n_samples, max_drags = 37, 70, 10
+    samples = np.zeros((batch, n_samples, 3), np.int32)
+    samples[..., 0] = rng.random((batch, n_samples)) < 0.8
+    samples[..., 1:] = rng.integers(100, 4000, (batch, n_samples, 2))
+    samples[0, :, 0] = 0                                   # nobody touches grid 0
+    samples[1, :, 0] = 1                                   # a continuous swipe: 69 records, 10 kept
+    d_drags = torch.zeros(batch, max_drags, 3, dtype=torch.int32, device="cuda")
+    d_counts = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    ctx.touch_to_drags(d_drags, d_counts, to_dev(samples), n_samples, batch, max_drags, 61, 81)
+    got = d_drags.cpu().numpy().view(synth.DRAG_DTYPE).reshape(batch, max_drags)
+    counts = d_counts.cpu().numpy()
+    for b in range(batch):
+        script = [tuple(int(x) for x in r) for r in samples[b]]
+        if getattr(oracle, "ref", None) is not None and oracle.ref.has_ino:
+            want = oracle.ref.ino_touch(script)            # the sketch itself: its queue holds 10
+        else:
+            want = synth.touch_drags(script, 61, 81)[:max_drags]
+        assert counts[b] == len(want), f"grid {b}: {counts[b]} records, want {len(want)}"
+        assert_bit_equal(got[b, :len(want)].view(np.uint8), want.view(np.uint8), f"grid {b}")
+    assert counts[0] == 0 and counts[1] == 10
+
+
+def test_ensemble_seeded_and_driven_on_device(ctx, oracle):
+    """setup() -> touch_routine() -> loop() x 3 without leaving the device == the same chain on the CPU checker."""
+    from esp32_fluid_simulation_b200 import synth
+    rng = np.random.default_rng(12)
+    batch, n_samples, max_drags, dim_x, dim_y, n_steps = 9, 12, 10, 61, 81, 3
+    v = torch.empty(batch, dim_y, dim_x, 2, device="cuda")
+    c = torch.empty(batch, dim_y, dim_x, 3, dtype=torch.int32, device="cuda")
+    ctx.init_color_wheel(v, c, batch, dim_x, dim_y)
+    samples = np.zeros((n_steps, batch, n_samples, 3), np.int32)
+    samples[..., 0] = rng.random((n_steps, batch, n_samples)) < 0.7
+    samples[..., 1] = rng.integers(300, 3600, (n_steps, batch, n_samples))       # inside the calibrated range: on the grid
+    samples[..., 2] = rng.integers(300, 3700, (n_steps, batch, n_samples))
+    d_drags = torch.zeros(n_steps, batch, max_drags, 3, dtype=torch.int32, device="cuda")
+    d_counts = torch.zeros(n_steps, batch, dtype=torch.int32, device="cuda")
+    d_samples = to_dev(samples)
+    for s in range(n_steps):
+        ctx.touch_to_drags(d_drags[s], d_counts[s], d_samples[s], n_samples, batch, max_drags, dim_x, dim_y)
+    ctx.ensemble_step_dev(v, c, d_drags, d_counts, max_drags, batch, dim_x, dim_y, DT, 1.0, 10, 1.96, n_steps)
+    gv, gc = to_host(v), to_host(c, np.uint32)
+    for b in range(batch):
+        ov, oc = oracle.init_color_wheel(dim_x, dim_y)
+        for s in range(n_steps):
+            dr = synth.touch_drags([tuple(int(x) for x in r) for r in samples[s, b]], dim_x, dim_y)[:max_drags]
+            ov, oc = oracle.step(ov, oc, dr, DT, 1.0, 10, 1.96)
+        assert_bit_equal(gv[b], ov, f"grid {b} velocity")
+        assert_bit_equal(gc[b], oc, f"grid {b} dye")
