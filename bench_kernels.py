@@ -75,6 +75,11 @@ def main():
         rec("calculate_divergence" + tag, timeit(stream, lambda: ctx.calculate_divergence(d, v, nx, ny, 1.0)), 12)
         rec("subtract_gradient" + tag, timeit(stream, lambda: ctx.subtract_gradient(v2, p, nx, ny, 1.0)), 20)
         rec("advect_rgb_uq32" + tag, timeit(stream, lambda: ctx.advect(c2, c, v, nx, ny, synth.DT, False)), 32)
+        rec("advect_drags_divergence" + tag, timeit(stream, lambda: ctx.advect_drags_divergence(v2, d, v, synth.drags(nx, ny, 0), nx, ny, synth.DT, 1.0)), 28)
+        frame = torch.empty((nx - 1) * 4, (ny - 1) * 4, dtype=torch.int16, device="cuda")
+        rec("upscale4_rgb565" + tag, timeit(stream, lambda: ctx.upscale4_rgb565(frame, c, nx, ny)), 44)
+        rec("advect_rgb_frame (advect + frame in one kernel)" + tag,
+            timeit(stream, lambda: ctx.advect_rgb_frame(c2, frame, c, v, nx, ny, synth.DT, False)), 32 + 32)
 
     def run_sor(tag=""):
         ms = timeit(stream, lambda: ctx.poisson_solve(p, d, nx, ny, 1.0, args.iters, 1.96), reps=5, warm=2)

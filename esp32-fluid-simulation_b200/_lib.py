@@ -37,7 +37,7 @@ class Tile(C.Structure):
 class DistConfig(C.Structure):
     """fs_dist_config"""
     _fields_ = [(n, C.c_int) for n in ("gdim_x", "gdim_y", "world", "rank", "px", "py", "ghost", "advect_halo",
-                                      "iters")] + [(n, C.c_float) for n in ("dt", "dx", "omega")]
+                                      "iters")] + [(n, C.c_float) for n in ("dt", "dx", "omega")] + [("frame", C.c_int)]
 
 
 class DistInfo(C.Structure):
@@ -82,6 +82,8 @@ def lib() -> C.CDLL:
         "fs_poisson_residual": ([C.POINTER(f), C.POINTER(C.c_double), vp, vp, I, I, f, vp], I),
         "fs_step": ([vp, vp, vp, I, I, I, f, f, I, f, vp, vp, vp], I),
         "fs_advect_drags_divergence": ([vp, vp, vp, vp, I, I, I, f, f, vp], I),
+        "fs_advect_rgb_frame": ([vp, vp, vp, vp, I, I, f, I, vp], I),
+        "fs_step_frame": ([vp, vp, vp, vp, vp, I, I, I, f, f, I, f, vp, vp, vp], I),
         "fs_step_pingpong": ([vp, vp, vp, vp, I, I, I, f, f, I, f, vp, vp, vp], I),
         "fs_upscale4_rgb565": ([vp, vp, I, I, vp], I),
         "fs_ensemble_step": ([vp, vp, vp, vp, I, I, I, I, f, f, I, f, I, vp], I),
@@ -120,6 +122,7 @@ def lib() -> C.CDLL:
         "fs_dist_upload": ([vp, vp, vp], I),
         "fs_dist_download": ([vp, vp, vp, vp, vp], I),
         "fs_dist_device_fields": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)], I),
+        "fs_dist_frame": ([vp, C.POINTER(vp), C.POINTER(I), C.POINTER(I)], I),
         "fs_dist_step": ([vp, vp, I], I),
         "fs_dist_check": ([vp], I),
     }

@@ -22,6 +22,7 @@
 #include "kernels.h"
 #include "stencil.cuh"
 #include "tma.cuh"
+#include "upscale.cuh"
 
 namespace fs {
 
@@ -352,6 +353,129 @@ advect_div_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_c
     }
 }
 
+// ---- fused: advect dye (ino:282) + the 4x RGB565 frame of the NEW dye (draw_routine, ino:116-177) --------
+// The CTA advects its 64x32 tile PLUS the next row and column (the far corners of its last cells) into
+// shared memory, stores the tile's dye, and renders its 64x32 cells straight from shared memory: the
+// frame never re-reads the dye (12 of the stand-alone upscale's 44 B/node) and costs no extra launch.
+// On a decomposed grid the extra row/column lie in the neighbour's rectangle: they are recomputed here
+// (same inputs, same bits), which needs the dye ghosts one node wider than the advect halo.
+constexpr int FR_NX = AT_TX + 1, FR_NY = AT_TY + 1;                         // advected nodes per CTA
+constexpr int FR_W = ((FR_NX + 2 * AT_HALO + 1 + 3) / 4) * 4;              // staged source tile (nodes)
+constexpr int FR_H = FR_NY + 2 * AT_HALO + 1;
+constexpr int FR_ROW_WORDS = FR_W * 3;
+constexpr int FR_IN_BYTES = FR_ROW_WORDS * FR_H * 4;
+constexpr int FR_EXT_PITCH = FR_NX * 3;                                    // 195 words: odd multiple of 3, conflict-free columns
+constexpr int FR_ITERS = (FR_NX * FR_NY + AT_THREADS - 1) / AT_THREADS;
+static_assert(FR_ROW_WORDS <= 256, "TMA box dimension limit");
+
+struct FrameAdvectArgs {
+    uint32_t *next_c;
+    const uint32_t *c;
+    const float2 *vel;
+    uint16_t *frame;        // first pixel of the cell at the compute rectangle's first node
+    size_t frame_pitch;     // pixels per image row
+    Geo g;
+    float dt;
+    int no_slip;
+    int frame_aligned8;
+    int *status;
+};
+
+__global__ void __launch_bounds__(AT_THREADS)
+advect_rgb_frame_kernel(const __grid_constant__ CUtensorMap in_map, const FrameAdvectArgs a)
+{
+    using P = RgbPayload;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint32_t *tile = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *ext = reinterpret_cast<uint32_t *>(smem + ((FR_IN_BYTES + 127) & ~127));   // [FR_NY][FR_EXT_PITCH]
+    __shared__ __align__(8) uint64_t bar;
+
+    const Geo &g = a.g;
+    const int tx0 = g.x0 + blockIdx.x * AT_TX, ty0 = g.y0 + blockIdx.y * AT_TY;
+    const int bx0 = tx0 - AT_HALO, by0 = ty0 - AT_HALO;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, FR_IN_BYTES);
+        tma_load_2d(tile, &in_map, bx0 * 3, by0, &bar);
+    }
+    // nodes this CTA advects: its tile + the next row/column, inside the compute rectangle grown by one
+    // node (and inside the window)
+    const int lim_x = min(g.x1 + 1, g.nx), lim_y = min(g.y1 + 1, g.ny);
+    float2 vel[FR_ITERS];
+#pragma unroll
+    for (int it = 0; it < FR_ITERS; it++) {
+        const int k = threadIdx.x + it * AT_THREADS;
+        const int ny = k / FR_NX, nx = k - ny * FR_NX;
+        const int lx = tx0 + nx, ly = ty0 + ny;
+        vel[it] = (k < FR_NX * FR_NY && lx < lim_x && ly < lim_y) ? __ldg(a.vel + (size_t)ly * g.nx + lx) : make_float2(0.f, 0.f);
+    }
+    mbar_wait(&bar, 0);
+
+    TileFetch<P, FR_W, FR_H> fetch{tile, a.c, bx0, by0, g.ox, g.oy, g.nx, g.vx0, g.vy0, g.vx1 - g.vx0, g.vy1 - g.vy0, a.status};
+    const int tx_lo = max(0, g.vx0 - bx0), tx_hi = min(FR_W - 1, g.vx1 - 1 - bx0);
+    const int ty_lo = max(0, g.vy0 - by0), ty_hi = min(FR_H - 1, g.vy1 - 1 - by0);
+    const float x_max = (float)(g.GX - 1), y_max = (float)(g.GY - 1);
+#pragma unroll
+    for (int it = 0; it < FR_ITERS; it++) {
+        const int k = threadIdx.x + it * AT_THREADS;
+        if (k >= FR_NX * FR_NY) break;
+        const int ny = k / FR_NX, nx = k - ny * FR_NX;
+        const int lx = tx0 + nx, ly = ty0 + ny;
+        uint32_t out[3] = {0u, 0u, 0u};
+        if (lx < lim_x && ly < lim_y) {
+            float si, sj;
+            backtrace(si, sj, g.ox + lx, g.oy + ly, vel[it], a.dt);
+            const float fi = floorf(si), fj = floorf(sj);
+            const int tx = (int)fi - g.ox - bx0, ty = (int)fj - g.oy - by0;
+            const bool interior = si >= 0.0f && si < x_max && sj >= 0.0f && sj < y_max;
+            if (interior && tx >= tx_lo && tx < tx_hi && ty >= ty_lo && ty < ty_hi) {
+                const float di = __fsub_rn(si, fi), dj = __fsub_rn(sj, fj);
+                const float wi = __fsub_rn(1.0f, di), wj = __fsub_rn(1.0f, dj);
+                const uint32_t *q = tile + ty * FR_ROW_WORDS + tx * 3;
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    const float a11 = uq32_to_float(q[ch]), a21 = uq32_to_float(q[3 + ch]);
+                    const float a12 = uq32_to_float(q[FR_ROW_WORDS + ch]);
+                    const float a22 = uq32_to_float(q[FR_ROW_WORDS + 3 + ch]);
+                    out[ch] = uq32_from_float(mixf(wi, di, mixf(wj, dj, a11, a12), mixf(wj, dj, a21, a22)));
+                }
+            } else {
+                sample_slow<P>(out, fetch, si, sj, g.GX, g.GY, a.no_slip != 0);
+            }
+            if (nx < AT_TX && ny < AT_TY && lx < g.x1 && ly < g.y1) {      // the tile itself: the advected dye
+                uint32_t *q = a.next_c + ((size_t)ly * g.nx + lx) * 3;
+                q[0] = out[0]; q[1] = out[1]; q[2] = out[2];
+            }
+        }
+        uint32_t *e = ext + ny * FR_EXT_PITCH + nx * 3;
+        e[0] = out[0]; e[1] = out[1]; e[2] = out[2];
+    }
+    __syncthreads();
+
+    // ---- frame: lane = cell column (j), warp = cell rows (i); a warp writes 256 contiguous bytes per image row ----
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int ly = ty0 + lane, gj = g.oy + ly;
+    if (ly >= g.y1 || gj >= g.GY - 1) return;                              // no cell starts at the last node column
+    for (int ci = w; ci < AT_TX; ci += AT_THREADS / 32) {
+        const int lx = tx0 + ci, gi = g.ox + lx;
+        if (lx >= g.x1 || gi >= g.GX - 1) break;
+        uint32_t c11[3], c12[3], c21[3], c22[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            c11[ch] = ext[lane * FR_EXT_PITCH + ci * 3 + ch];              // (i,   j)
+            c12[ch] = ext[(lane + 1) * FR_EXT_PITCH + ci * 3 + ch];        // (i,   j+1)
+            c21[ch] = ext[lane * FR_EXT_PITCH + (ci + 1) * 3 + ch];        // (i+1, j)
+            c22[ch] = ext[(lane + 1) * FR_EXT_PITCH + (ci + 1) * 3 + ch];  // (i+1, j+1)
+        }
+        upscale_cell_rgb565(a.frame + 4 * (size_t)(lx - g.x0) * a.frame_pitch + 4 * (size_t)(ly - g.y0), a.frame_pitch,
+                            a.frame_aligned8 != 0, c11, c12, c21, c22);
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------
 
 template <class P>
@@ -445,6 +569,28 @@ int launch_advect_div_tma(const Launch &L, float2 *v_out, const float2 *v_in, fl
 
 int advect_div_max_drags() { return AD_MAX_DRAGS; }
 
+// frame_cells_y = number of cell columns (j) of the frame = its row pitch / 4
+int launch_advect_rgb_frame(const Launch &L, uint32_t *next_c, uint16_t *frame, int frame_cells_y, const uint32_t *c,
+                            const float2 *vel, const Geo &g, float dt, bool no_slip, int *status)
+{
+    const int w = g.x1 - g.x0, h = g.y1 - g.y0;
+    if (w <= 0 || h <= 0) return 0;
+    CUtensorMap in_map;
+    if (!tma_make_map_2d(&in_map, c, (uint64_t)g.nx * 3, g.ny, (uint64_t)g.nx * 3, FR_ROW_WORDS, FR_H))
+        return (int)cudaErrorInvalidValue;
+    FrameAdvectArgs a;
+    a.next_c = next_c; a.c = c; a.vel = vel; a.frame = frame; a.frame_pitch = 4 * (size_t)frame_cells_y;
+    a.g = g; a.dt = dt; a.no_slip = no_slip ? 1 : 0; a.status = status;
+    a.frame_aligned8 = (uintptr_t)frame % 8 == 0;
+    const size_t smem = ((FR_IN_BYTES + 127) & ~127) + (size_t)FR_NY * FR_EXT_PITCH * 4;
+    cudaError_t e = cudaFuncSetAttribute(advect_rgb_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((w + AT_TX - 1) / AT_TX, (h + AT_TY - 1) / AT_TY);
+    advect_rgb_frame_kernel<<<grid, AT_THREADS, smem, L.stream>>>(in_map, a);
+    ++*L.launches;
+    return (int)cudaGetLastError();
+}
+
 // dye advect with the gradient-subtract of the projection folded in: v_out = v_tmp - grad p, and the
 // dye is advected with v_out (ino:276 + ino:282 in one pass over the grid)
 int launch_advect_rgb_tma_grad(const Launch &L, uint32_t *next_c, const uint32_t *c, float2 *v_out,
@@ -459,6 +605,7 @@ int preload_advect_tma_kernels()
     FS_PRELOAD(advect_tma_kernel<Vec2Payload>);
     FS_PRELOAD(advect_tma_kernel<RgbPayload>);
     FS_PRELOAD(advect_div_tma_kernel);
+    FS_PRELOAD(advect_rgb_frame_kernel);
     return 0;
 }
 

@@ -188,7 +188,7 @@ int fs_ctx_create(fs_ctx **out, int device, void *stream)
     ctx->opt_halo_timeout_ms = 10000;
     ctx->opt_ens = 0;
     ctx->opt_advect = 1;
-    ctx->opt_fuse = 1;
+    ctx->opt_fuse = 5;
     cudaError_t e = cudaMalloc(&ctx->status_dev, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->maxdisp_dev, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->work_dev, WORK_SLOTS * sizeof(int));
@@ -381,6 +381,49 @@ int fs_advect_drags_divergence(fs_vec2f *v_out, float *div, const fs_vec2f *v_in
     if ((e = core_advect_vec2f(ctx, v_out, v_in, v_in, g, dt, 1, nullptr))) return e;
     if (n_drags > 0 && (e = launch_apply_drags(mk(ctx), (float2 *)v_out, drags, n_drags, g))) return e;
     return launch_divergence(mk(ctx), div, (const float2 *)v_out, g, dx);
+}
+
+// dye advect + frame: fused where the TMA kernel is legal, else advect followed by the stand-alone upscale
+static int core_advect_rgb_frame(fs_ctx *ctx, fs_rgb_uq32 *next_c, uint16_t *frame, const fs_rgb_uq32 *c, const fs_vec2f *vel,
+                                 int dim_x, int dim_y, float dt, int no_slip)
+{
+    const Geo g = geo_full(dim_x, dim_y);
+    if (ctx->opt_advect == 1 && (ctx->opt_fuse & 4) && advect_rgb_tma_legal((const uint32_t *)c, g))
+        return launch_advect_rgb_frame(mk(ctx), (uint32_t *)next_c, frame, dim_y - 1, (const uint32_t *)c, (const float2 *)vel,
+                                       g, dt, no_slip != 0, nullptr);
+    int e = core_advect_rgb(ctx, next_c, c, vel, g, dt, no_slip, nullptr);
+    if (e) return e;
+    return launch_upscale4_rgb565(mk(ctx), frame, (const uint32_t *)next_c, dim_x, dim_y);
+}
+
+int fs_advect_rgb_frame(fs_rgb_uq32 *next_c, uint16_t *frame, const fs_rgb_uq32 *c, const fs_vec2f *vel, int dim_x,
+                        int dim_y, float dt, int no_slip, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!next_c || !frame || !c || !vel || bad_dims(dim_x, dim_y) || next_c == c) return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    return core_advect_rgb_frame(ctx, next_c, frame, c, vel, dim_x, dim_y, dt, no_slip);
+}
+
+int fs_step_frame(fs_vec2f *v, const fs_rgb_uq32 *c_in, fs_rgb_uq32 *c_out, uint16_t *frame, const fs_drag *drags,
+                  int n_drags, int dim_x, int dim_y, float dt, float dx, int iters, float omega, float *p_out,
+                  float *div_out, fs_ctx *ctx)
+{
+    if (!ctx) return FS_ERR_NO_CONTEXT;
+    if (!v || !c_in || !c_out || !frame || c_in == c_out || n_drags < 0 || (n_drags > 0 && !drags) ||
+        bad_dims(dim_x, dim_y) || iters < 0)
+        return FS_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->device);
+    const size_t n = (size_t)dim_x * dim_y;
+    void *v_tmp, *p = p_out, *d = div_out;
+    int e;
+    if ((e = ensure(ctx, S_VTMP, n * sizeof(fs_vec2f), &v_tmp))) return e;
+    if (!p && (e = ensure(ctx, S_P, n * sizeof(float), &p))) return e;
+    if (!d && (e = ensure(ctx, S_DIV, n * sizeof(float), &d))) return e;
+    if ((e = core_step_velocity(ctx, v, (fs_vec2f *)v_tmp, drags, n_drags, geo_full(dim_x, dim_y), dt, dx, iters, omega,
+                                (float *)p, (float *)d)))
+        return e;
+    return core_advect_rgb_frame(ctx, c_out, frame, c_in, v, dim_x, dim_y, dt, 0);   // ino:282 + ino:116-177
 }
 
 int fs_step_pingpong(fs_vec2f *v, const fs_rgb_uq32 *c_in, fs_rgb_uq32 *c_out, const fs_drag *drags,

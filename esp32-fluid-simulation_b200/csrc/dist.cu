@@ -89,6 +89,8 @@ struct fs_dist {
     bool v_halo_ok;                    // the current velocity's ghosts are valid to width vw
     float *p_last;
     int has_l, has_r, has_d, has_u;
+    uint16_t *frame;                   // this rank's part of the RGB565 frame (cfg.frame), or nullptr
+    int cells_x, cells_y;
 };
 
 namespace {
@@ -229,10 +231,10 @@ int fs_dist_create(fs_dist **out, const fs_dist_config *cfg, fs_ctx *ctx)
     d->D = round_up4(need_d);
     d->A = cfg->world > 1 ? cfg->advect_halo : 0;
     d->vw = round_up4(d->D + 1 + d->A);
-    d->cw = round_up4(d->A);
+    d->cw = round_up4(d->A + (cfg->frame && cfg->world > 1 ? 1 : 0));   // the frame's far corners lie one node beyond
     // identical verdict on every rank: the widest exchanged strip must fit the ghosts AND the
     // narrowest rectangle of the decomposition (a strip is cut out of the sender's rectangle)
-    if (cfg->world > 1 && (d->vw > ghost || ghost > min_extent || d->n_pass > WORK_SLOTS)) {
+    if (cfg->world > 1 && (d->vw > ghost || d->cw > ghost || ghost > min_extent || d->n_pass > WORK_SLOTS)) {
         delete d;
         return FS_ERR_INVALID_ARG;
     }
@@ -284,6 +286,22 @@ int fs_dist_create(fs_dist **out, const fs_dist_config *cfg, fs_ctx *ctx)
             return e2;
         }
     }
+    d->frame = nullptr;
+    d->cells_x = (d->me.gx1 < cfg->gdim_x - 1 ? d->me.gx1 : cfg->gdim_x - 1) - d->me.gx0;
+    d->cells_y = (d->me.gy1 < cfg->gdim_y - 1 ? d->me.gy1 : cfg->gdim_y - 1) - d->me.gy0;
+    if (cfg->frame) {
+        if (d->me.nx < 64 || d->me.ny < 32 || d->cells_x < 1 || d->cells_y < 1) {   // the fused kernel's tile
+            cudaFree(d->arena);
+            delete d;
+            return FS_ERR_UNSUPPORTED;
+        }
+        e = cudaMalloc(&d->frame, (size_t)16 * d->cells_x * d->cells_y * sizeof(uint16_t));
+        if (e != cudaSuccess) {
+            cudaFree(d->arena);
+            delete d;
+            return (int)e;
+        }
+    }
     d->cur_v = d->cur_c = 0;
     d->connected = d->n_nb == 0;
     d->seq = 0;
@@ -302,7 +320,17 @@ int fs_dist_destroy(fs_dist *d)
     for (int k = 0; k < d->n_nb; k++)
         if (d->nb[k].opened) cudaIpcCloseMemHandle(d->nb[k].base);
     cudaFree(d->arena);
+    cudaFree(d->frame);
     delete d;
+    return FS_OK;
+}
+
+int fs_dist_frame(fs_dist *d, uint16_t **frame, int *rows, int *cols)
+{
+    if (!d || !d->frame) return FS_ERR_INVALID_ARG;
+    if (frame) *frame = d->frame;
+    if (rows) *rows = 4 * d->cells_x;
+    if (cols) *cols = 4 * d->cells_y;
     return FS_OK;
 }
 
@@ -529,7 +557,14 @@ int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags)
     // ---- 5. advect dye (ino:282, free-slip sampling) with the projected velocity -------------------------------
     Geo gc = gw;
     grow_rect(gw, d->cw, gc.vx0, gc.vy0, gc.vx1, gc.vy1);   // dye ghosts are valid to width cw
-    if ((e = core_advect_rgb(ctx, c2, c, v2, gc, cfg.dt, 0, ctx->status_dev))) return e;
+    if (d->frame) {   // + this rank's part of the 4x RGB565 frame, rendered from the tile in shared memory (ino:116-177)
+        if (!advect_rgb_tma_legal((const uint32_t *)c, gc)) return FS_ERR_UNSUPPORTED;
+        if ((e = launch_advect_rgb_frame(mk(ctx), (uint32_t *)c2, d->frame, d->cells_y, (const uint32_t *)c, (const float2 *)v2,
+                                         gc, cfg.dt, false, ctx->status_dev)))
+            return e;
+    } else if ((e = core_advect_rgb(ctx, c2, c, v2, gc, cfg.dt, 0, ctx->status_dev))) {
+        return e;
+    }
 
     d->cur_v ^= 1;    // ino:255 / ino:286: the pointer swaps
     d->cur_c ^= 1;

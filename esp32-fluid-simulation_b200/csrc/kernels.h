@@ -35,6 +35,11 @@ int launch_advect_div_tma(const Launch &L, float2 *v_out, const float2 *v_in, fl
                           int n_drags, const Geo &g, float dt, float dx, const int *store_rect = nullptr,
                           int *status = nullptr);
 int advect_div_max_drags();
+// fused dye advect + 4x RGB565 frame of the advected dye (ino:282 + ino:116-177): the frame covers the
+// cells that start at the nodes of g's compute rectangle (needs the dye valid one node beyond the
+// advect halo); frame = first pixel of the cell at (x0, y0), frame_cells_y = its cell columns
+int launch_advect_rgb_frame(const Launch &L, uint32_t *next_c, uint16_t *frame, int frame_cells_y, const uint32_t *c,
+                            const float2 *vel, const Geo &g, float dt, bool no_slip, int *status);
 int launch_advect_rgb_tma_grad(const Launch &L, uint32_t *next_c, const uint32_t *c, float2 *v_out,
                                const float2 *v_tmp, const float *p, const Geo &g, float dt, float dx,
                                bool no_slip, int *status);

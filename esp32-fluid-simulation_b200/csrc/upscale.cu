@@ -10,6 +10,7 @@
 // The ramps are ACCUMULATED (c += dc, ino:137,151,160), not evaluated as
 // c + k*dc; the adds are replayed in the reference's order.
 #include "kernels.h"
+#include "upscale.cuh"
 
 namespace fs {
 
@@ -18,7 +19,7 @@ constexpr int UP_PITCH = 33 * 3;    // words per staged row (odd => conflict-fre
 
 __global__ void __launch_bounds__(256)
 upscale4_rgb565_kernel(uint16_t *__restrict__ out, const uint32_t *__restrict__ c, int dim_x,
-                       int dim_y)
+                       int dim_y, bool aligned8)
 {
     __shared__ uint32_t s[33 * UP_PITCH];
     const int i0 = blockIdx.x * UP_T, j0 = blockIdx.y * UP_T;
@@ -40,49 +41,15 @@ upscale4_rgb565_kernel(uint16_t *__restrict__ out, const uint32_t *__restrict__ 
     for (int ti = threadIdx.y; ti < UP_T; ti += 8) {
         const int i = i0 + ti;
         if (i >= dim_x - 1) break;
-        uint32_t px[4][4][3];
+        uint32_t c11[3], c12[3], c21[3], c22[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
-            const float c11 = __uint2float_rn(s[tj * UP_PITCH + ti * 3 + ch]);           // (i,   j)
-            const float c12 = __uint2float_rn(s[(tj + 1) * UP_PITCH + ti * 3 + ch]);     // (i,   j+1)
-            const float c21 = __uint2float_rn(s[tj * UP_PITCH + (ti + 1) * 3 + ch]);     // (i+1, j)
-            const float c22 = __uint2float_rn(s[(tj + 1) * UP_PITCH + (ti + 1) * 3 + ch]);
-            float left[4], right[4];
-            float a = c11;
-            const float da = __fmul_rn(__fsub_rn(c21, c11), 0.25f);  // ino:134
-            float b = c12;
-            const float db = __fmul_rn(__fsub_rn(c22, c12), 0.25f);  // ino:148
-#pragma unroll
-            for (int ii = 0; ii < 4; ii++) {
-                left[ii] = a;
-                a = __fadd_rn(a, da);
-                right[ii] = b;
-                b = __fadd_rn(b, db);
-            }
-#pragma unroll
-            for (int ii = 0; ii < 4; ii++) {
-                float r = left[ii];
-                const float dr = __fmul_rn(__fsub_rn(right[ii], r), 0.25f);  // ino:157
-#pragma unroll
-                for (int jj = 0; jj < 4; jj++) {
-                    px[ii][jj][ch] = __float2uint_rz(__fadd_rn(r, 0.5f));     // ino:168
-                    r = __fadd_rn(r, dr);
-                }
-            }
+            c11[ch] = s[tj * UP_PITCH + ti * 3 + ch];              // (i,   j)
+            c12[ch] = s[(tj + 1) * UP_PITCH + ti * 3 + ch];        // (i,   j+1)
+            c21[ch] = s[tj * UP_PITCH + (ti + 1) * 3 + ch];        // (i+1, j)
+            c22[ch] = s[(tj + 1) * UP_PITCH + (ti + 1) * 3 + ch];  // (i+1, j+1)
         }
-#pragma unroll
-        for (int ii = 0; ii < 4; ii++) {
-            uint32_t w[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-                uint32_t v565 = ((px[ii][jj][0] & 0xF8000000u) >> 16) |
-                                ((px[ii][jj][1] & 0xFC000000u) >> 21) |
-                                ((px[ii][jj][2] & 0xF8000000u) >> 27);       // ino:170-172
-                w[jj] = ((v565 & 0xFFu) << 8) | (v565 >> 8);                 // ino:173
-            }
-            uint2 q = make_uint2(w[0] | (w[1] << 16), w[2] | (w[3] << 16));
-            *reinterpret_cast<uint2 *>(out + (4 * (size_t)i + ii) * pitch + 4 * (size_t)j) = q;
-        }
+        upscale_cell_rgb565(out + 4 * (size_t)i * pitch + 4 * (size_t)j, pitch, aligned8, c11, c12, c21, c22);
     }
 }
 
@@ -90,7 +57,9 @@ int launch_upscale4_rgb565(const Launch &L, uint16_t *out, const uint32_t *c, in
 {
     if (dim_x < 2 || dim_y < 2) return 0;
     dim3 block(32, 8), grid((dim_x - 1 + UP_T - 1) / UP_T, (dim_y - 1 + UP_T - 1) / UP_T);
-    upscale4_rgb565_kernel<<<grid, block, 0, L.stream>>>(out, c, dim_x, dim_y);
+    // 8-byte pixel-quad stores need an 8-byte aligned frame (a uint16_t* into a larger buffer may not be)
+    const bool aligned8 = (uintptr_t)out % 8 == 0;
+    upscale4_rgb565_kernel<<<grid, block, 0, L.stream>>>(out, c, dim_x, dim_y, aligned8);
     ++*L.launches;
     return (int)cudaGetLastError();
 }

@@ -444,7 +444,7 @@ class NativeDist:
 
     def __init__(self, ctx, gdim_x: int, gdim_y: int, world: int, rank: int, iters: int, ghost: int = 64,
                  advect_halo: int = 40, grid: tuple[int, int] | None = None,
-                 dt=np.float32(1 / 30.0), dx=np.float32(1.0), omega=np.float32(1.96)):
+                 dt=np.float32(1 / 30.0), dx=np.float32(1.0), omega=np.float32(1.96), frame: bool = False):
         import ctypes as C
 
         from . import _lib
@@ -452,7 +452,7 @@ class NativeDist:
         self._L = _lib.lib()
         px, py = grid or (0, 0)
         cfg = _lib.DistConfig(gdim_x, gdim_y, world, rank, px, py, ghost, advect_halo, iters, float(dt), float(dx),
-                              float(omega))
+                              float(omega), int(bool(frame)))
         h = C.c_void_p()
         _lib.check(self._L.fs_dist_create(C.byref(h), C.byref(cfg), ctx._h), "fs_dist_create")
         self._h = h
@@ -531,6 +531,13 @@ class NativeDist:
         self._lib.check(self._L.fs_dist_device_fields(self._h, C.byref(v), C.byref(c), C.byref(p), C.byref(d)),
                         "fs_dist_device_fields")
         return v.value, c.value, p.value, d.value
+
+    def frame(self):
+        """(device address, rows, cols) of this rank's part of the RGB565 frame (created with frame=True)."""
+        C = self._C
+        p, r, c = C.c_void_p(), C.c_int(), C.c_int()
+        self._lib.check(self._L.fs_dist_frame(self._h, C.byref(p), C.byref(r), C.byref(c)), "fs_dist_frame")
+        return p.value, r.value, c.value
 
     def step(self, drags=None):
         from .ops import _drags
@@ -626,8 +633,9 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
 
     ctx = fb.Context(local_rank, torch.cuda.current_stream(dev))
     sor_t = ctx.get_option("sor_t")
+    want_frame = bool(getattr(args, "upscale", False))
     sim = NativeDist(ctx, gx, gy, world, rank, iters, ghost=ghost, advect_halo=halo, dt=synth.DT, dx=synth.DX,
-                     omega=synth.OMEGA)
+                     omega=synth.OMEGA, frame=want_frame)
     handles = [None] * world
     dist.all_gather_object(handles, sim.ipc_handle())
     sim.connect(handles)
@@ -636,18 +644,10 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
     hc = torch.from_numpy(synth.dye(gx, gy, window=(w.ox, w.oy, w.nx, w.ny)).view(np.int32)).pin_memory()
     sim.upload(hv, hc)
     drags = [synth.drags(gx, gy, s, n=n_drags) for s in range(args.warmup + args.steps)]
-    frame = None
-    if getattr(args, "upscale", False):
-        # the rank's part of the 4x RGB565 frame (ino:116-177): upscale the window, ghosts included
-        frame = torch.empty((w.nx - 1) * 4, (w.ny - 1) * 4, dtype=torch.int16, device=dev)
-
-    def dye_window():
-        return torch.as_tensor(_device_view(sim.device_fields()[1], (w.ny, w.nx, 3), "<i4"), device=dev)
+    frame = sim.frame() if want_frame else None   # this rank's part of the 4x RGB565 frame, rendered inside the dye advect
 
     def one_step(k):
         sim.step(drags[k])
-        if frame is not None:
-            ctx.upscale4_rgb565(frame, dye_window(), w.nx, w.ny)
 
     for s in range(args.warmup):
         one_step(s)
@@ -762,7 +762,7 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
         "dtype": "f32+uq32", "data": "synthetic",
         "config": {"workload": f"{gx}x{gy} grid block-decomposed {px}x{py}, {own_w}x{own_h} nodes per GPU, "
                                f"{iters} SOR iterations, velocity + dye advection"
-                               + (", 4x RGB565 frame every step" if frame is not None else ""),
+                               + (", 4x RGB565 frame every step (rendered inside the dye advect)" if frame is not None else ""),
                    "grid": [gx, gy], "process_grid": [px, py], "ghost": ghost, "sor_t": sor_t,
                    "halo": "fs_dist (C++): SOR passes fused with their NVLink peer-store halo exchange; one exchange "
                            "kernel for velocity + dye",

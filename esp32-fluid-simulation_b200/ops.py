@@ -214,6 +214,21 @@ class Context:
         check(self._L.fs_advect_drags_divergence(a_o, a_d, a_i, d.ctypes.data if nd else None, nd, dim_x, dim_y, dt, dx,
                                                  self._h), "fs_advect_drags_divergence")
 
+    def advect_rgb_frame(self, next_c, frame, c, vel, dim_x, dim_y, dt, no_slip=False):
+        """Dye advect + the 4x RGB565 frame of the advected dye in one kernel (device tensors)."""
+        n = dim_x * dim_y
+        check(self._L.fs_advect_rgb_frame(_ptr(next_c, "uint32", 3 * n)[0], _ptr(frame, "uint16", 16 * (dim_x - 1) * (dim_y - 1))[0],
+                                          _ptr(c, "uint32", 3 * n)[0], _ptr(vel, "float32", 2 * n)[0], dim_x, dim_y, dt,
+                                          int(bool(no_slip)), self._h), "fs_advect_rgb_frame")
+
+    def step_frame(self, v, c_in, c_out, frame, drags, dim_x, dim_y, dt, dx, iters, omega):
+        """loop() + draw_routine's arithmetic: the step, and the RGB565 frame of its new dye (device tensors)."""
+        n = dim_x * dim_y
+        d, nd = _drags(drags)
+        check(self._L.fs_step_frame(_ptr(v, "float32", 2 * n)[0], _ptr(c_in, "uint32", 3 * n)[0], _ptr(c_out, "uint32", 3 * n)[0],
+                                    _ptr(frame, "uint16", 16 * (dim_x - 1) * (dim_y - 1))[0], d.ctypes.data if nd else None, nd,
+                                    dim_x, dim_y, dt, dx, iters, omega, None, None, self._h), "fs_step_frame")
+
     def step_pingpong(self, v, c_in, c_out, drags, dim_x, dim_y, dt, dx, iters, omega, p_out=None, div_out=None):
         """loop() body with the dye going c_in -> c_out (the caller swaps, ino:286); device tensors."""
         n = dim_x * dim_y

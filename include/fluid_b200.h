@@ -77,7 +77,9 @@ int  fs_ctx_synchronize(fs_ctx *ctx);
  *   "advect" : 0 = direct L1/L2 gather, 1 = TMA-staged shared-memory tile (default where legal)
  *   "fuse"   : bit mask for fs_step: 1 = drags + divergence folded into the velocity advect, 2 =
  *              gradient-subtract folded into the dye advect (measured slower than the stand-alone
- *              gradient kernel, which runs at the HBM roofline); 0 = one kernel per operator; default 1
+ *              gradient kernel, which runs at the HBM roofline), 4 = the RGB565 frame rendered inside
+ *              the dye advect (fs_step_frame, fs_advect_rgb_frame, fs_dist with frame = 1);
+ *              0 = one kernel per operator; default 5
  *   "sor_grid_limit": cap on the persistent SOR grid, 0 (default) = one CTA per SM; used when several
  *              emulated ranks share one device */
 int  fs_ctx_set_option(fs_ctx *ctx, const char *name, int value);
@@ -139,6 +141,17 @@ int fs_advect_drags_divergence(fs_vec2f *v_out, float *div, const fs_vec2f *v_in
 int fs_step_pingpong(fs_vec2f *v, const fs_rgb_uq32 *c_in, fs_rgb_uq32 *c_out, const fs_drag *drags,
                      int n_drags, int dim_x, int dim_y, float dt, float dx, int iters, float omega,
                      float *p_out, float *div_out, fs_ctx *ctx);
+/* Dye advect (ino:282) with the 4x RGB565 frame of the ADVECTED dye (draw_routine arithmetic,
+ * ino:116-177) produced in the same kernel: the frame is rendered from the tile while it is still in
+ * shared memory instead of re-reading the dye (fuse bit 4; otherwise advect + fs_upscale4_rgb565).
+ * frame layout as fs_upscale4_rgb565. */
+int fs_advect_rgb_frame(fs_rgb_uq32 *next_c, uint16_t *frame, const fs_rgb_uq32 *c, const fs_vec2f *vel,
+                        int dim_x, int dim_y, float dt, int no_slip, fs_ctx *ctx);
+/* fs_step_pingpong that also hands the frame of the new dye to the display side (the sketch's
+ * color_produced hand-off, ino:285-288): loop() + draw_routine's arithmetic in one call. */
+int fs_step_frame(fs_vec2f *v, const fs_rgb_uq32 *c_in, fs_rgb_uq32 *c_out, uint16_t *frame,
+                  const fs_drag *drags, int n_drags, int dim_x, int dim_y, float dt, float dx, int iters,
+                  float omega, float *p_out, float *div_out, fs_ctx *ctx);
 /* draw_routine arithmetic, ino:116-177: 4x bilinear upscale of the dye, UQ32
  * round, RGB565 pack, byte swap.  out is (dim_x-1)*4 rows x (dim_y-1)*4 columns
  * of uint16, row pitch (dim_y-1)*4 (image rows run along the sim's fast axis). */
@@ -280,6 +293,8 @@ typedef struct fs_dist_config {
                                step raises FS_ERR_HALO_OVERRUN.  Needs A + 2*sor_t + 2 <= ghost */
     int iters;              /* SOR iterations per step (the context's "sor_t" of them per pass) */
     float dt, dx, omega;
+    int frame;              /* 1 = also render this rank's part of the 4x RGB565 frame every step (fused into
+                               the dye advect, ino:116-177); read it with fs_dist_frame */
 } fs_dist_config;
 typedef struct fs_dist_info_t {
     int px, py, n_neighbours;
@@ -307,6 +322,9 @@ int fs_dist_upload(fs_dist *d, const fs_vec2f *v_window, const fs_rgb_uq32 *c_wi
 int fs_dist_download(fs_dist *d, fs_vec2f *v_rect, fs_rgb_uq32 *c_rect, float *p_rect, float *div_rect);
 /* device pointers of the CURRENT windows (they alternate from step to step like ino:255,286) */
 int fs_dist_device_fields(fs_dist *d, fs_vec2f **v, fs_rgb_uq32 **c, float **p, float **div);
+/* this rank's part of the frame: the cells that START in its rectangle, 4*cells_x rows x 4*cells_y columns
+ * of RGB565 (device pointer, dense, row pitch 4*cells_y); global pixel (4*gx0 + r, 4*gy0 + c) */
+int fs_dist_frame(fs_dist *d, uint16_t **frame, int *rows, int *cols);
 /* one loop() body; `drags` = the step's whole queue (HOST array; every rank passes all records) */
 int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags);
 /* FS_OK, FS_ERR_HALO_OVERRUN or FS_ERR_HALO_TIMEOUT since the last check; synchronises */

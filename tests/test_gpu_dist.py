@@ -64,7 +64,7 @@ def test_tile_overrun_is_reported(ctx):
 # spins on flags that rank B's kernel sets, so every rank's persistent grid is capped at SMs/N
 # ("sor_grid_limit") to keep all of them resident.
 
-def _native_run(world, gx, gy, iters, sor_t, ghost, halo, steps, v0, c0, drags, grid=None, fuse=1, upload_every_step=False):
+def _native_run(world, gx, gy, iters, sor_t, ghost, halo, steps, v0, c0, drags, grid=None, fuse=1, frame=False):
     import esp32_fluid_simulation_b200 as fb
     from esp32_fluid_simulation_b200.dist import NativeDist
     props = torch.cuda.get_device_properties(0)
@@ -76,7 +76,7 @@ def _native_run(world, gx, gy, iters, sor_t, ghost, halo, steps, v0, c0, drags, 
         ctx.set_option("halo_timeout_ms", 20000)
         ctx.set_option("sor_grid_limit", max(1, props.multi_processor_count // world))
         ctxs.append(ctx)
-        sims.append(NativeDist(ctx, gx, gy, world, r, iters, ghost=ghost, advect_halo=halo, grid=grid))
+        sims.append(NativeDist(ctx, gx, gy, world, r, iters, ghost=ghost, advect_halo=halo, grid=grid, frame=frame))
     for s in sims:
         s.connect_local(sims)
     for s in sims:
@@ -105,6 +105,16 @@ def _native_run(world, gx, gy, iters, sor_t, ghost, halo, steps, v0, c0, drags, 
         ys, xs = slice(w.oy + w.y0, w.oy + w.y1), slice(w.ox + w.x0, w.ox + w.x1)
         gv[ys, xs], gc[ys, xs], gp[ys, xs], gd[ys, xs] = out["v"], out["c"], out["p"], out["d"]
     info = sims[0].info
+    if frame:                                  # assemble the global RGB565 frame from the ranks' parts
+        img = np.zeros(((gx - 1) * 4, (gy - 1) * 4), np.uint16)
+        for s in sims:
+            ptr, rows, cols = s.frame()
+            from esp32_fluid_simulation_b200.dist import _device_view
+            part = torch.as_tensor(_device_view(ptr, (rows, cols), "<i2"), device="cuda").cpu().numpy().view(np.uint16)
+            w = s.window
+            r0, c0_ = 4 * (w.ox + w.x0), 4 * (w.oy + w.y0)
+            img[r0:r0 + rows, c0_:c0_ + cols] = part
+        info["frame"] = img
     for s in sims:
         s.close()
     return gv, gc, gp, gd, info
@@ -151,3 +161,25 @@ def test_native_decomposed_overrun_is_reported():
     with pytest.raises(fb.FluidError) as e:
         _native_run(2, gx, gy, 6, 3, 32, 12, 1, v0, c0, [None])
     assert e.value.code == FS_ERR_HALO_OVERRUN
+
+
+@pytest.mark.parametrize("world,grid,gx,gy,iters,sor_t,ghost,halo", [
+    (2, None, 256, 192, 10, 2, 32, 16),
+    (4, None, 512, 384, 13, 4, 32, 12),
+    (8, None, 1024, 768, 20, 6, 32, 8),
+    (1, None, 300, 200, 11, 4, 0, 0),
+])
+def test_native_decomposed_frame(oracle, world, grid, gx, gy, iters, sor_t, ghost, halo):
+    """fs_dist with frame=1: every rank renders the cells that start in its rectangle inside its dye advect (the far
+    corners of its last cells are the neighbour's nodes, recomputed locally) — assembled == the reference's frame."""
+    from esp32_fluid_simulation_b200 import synth
+    v0, c0 = synth.velocity(gx, gy, vmax=150.0), synth.dye(gx, gy)
+    steps = 2
+    drags = [synth.drags(gx, gy, s, n=8, vmax=float(30 * (halo - 6)) if halo else 400.0) for s in range(steps)]
+    gv, gc, gp, gd, info = _native_run(world, gx, gy, iters, sor_t, ghost, halo, steps, v0, c0, drags, grid, frame=True)
+    ov, oc = v0.copy(), c0.copy()
+    for s in range(steps):
+        ov, oc = oracle.step(ov, oc, drags[s], DT, 1.0, iters, 1.96)
+    assert_bit_equal(gv, ov, "velocity")
+    assert_bit_equal(gc, oc, "dye")
+    assert_bit_equal(info["frame"], oracle.upscale4_rgb565(oc), "RGB565 frame")

@@ -214,7 +214,7 @@ def test_step_matches_oracle(ctx, oracle, shape, iters, steps, fuse):
         for name, g, w in zip("vcpd", got, (ov, oc, op, od)):
             assert_bit_equal(g, w, f"{name} after {steps} steps")
     finally:
-        ctx.set_option("fuse", 1)
+        ctx.set_option("fuse", 5)
 
 
 @pytest.mark.parametrize("shape", [(61, 81), (256, 192), (1000, 333), (1024, 512)])
@@ -477,3 +477,53 @@ def test_ensemble_seeded_and_driven_on_device(ctx, oracle):
             ov, oc = oracle.step(ov, oc, dr, DT, 1.0, 10, 1.96)
         assert_bit_equal(gv[b], ov, f"grid {b} velocity")
         assert_bit_equal(gc[b], oc, f"grid {b} dye")
+
+
+# ---- f1: the RGB565 frame rendered inside the dye advect (ino:282 + ino:116-177) -----------------------
+
+@pytest.mark.parametrize("fuse", [5, 1], ids=["frame-in-advect", "advect-then-upscale"])
+@pytest.mark.parametrize("shape", [(64, 32), (61, 81), (130, 70), (200, 67), (512, 300), (1024, 512)])
+def test_advect_rgb_frame(ctx, oracle, shape, fuse):
+    dim_x, dim_y = shape
+    v, c = rand_fields(31, dim_x, dim_y, 150.0)
+    c[0, 0] = 0xFFFFFFFF
+    ctx.set_option("fuse", fuse)
+    try:
+        out = torch.empty(dim_y, dim_x, 3, dtype=torch.int32, device="cuda")
+        frame = torch.zeros((dim_x - 1) * 4, (dim_y - 1) * 4, dtype=torch.int16, device="cuda")
+        ctx.advect_rgb_frame(out, frame, to_dev(c), to_dev(v), dim_x, dim_y, DT, False)
+    finally:
+        ctx.set_option("fuse", 5)
+    want = oracle.advect_rgb_uq32(c, v, DT, False)
+    assert_bit_equal(to_host(out, np.uint32), want, "advected dye")
+    assert_bit_equal(to_host(frame, np.uint16), oracle.upscale4_rgb565(want), "RGB565 frame")
+
+
+def test_step_frame(ctx, oracle):
+    """loop() + draw_routine(): fs_step_frame == the reference step followed by the reference's frame."""
+    from esp32_fluid_simulation_b200 import synth
+    dim_x, dim_y, iters, steps = 320, 200, 20, 3
+    v, c = synth.velocity(dim_x, dim_y, vmax=80.0), synth.dye(dim_x, dim_y)
+    dv, ca, cb = to_dev(v), to_dev(c), torch.empty(dim_y, dim_x, 3, dtype=torch.int32, device="cuda")
+    frame = torch.zeros((dim_x - 1) * 4, (dim_y - 1) * 4, dtype=torch.int16, device="cuda")
+    ov, oc = v.copy(), c.copy()
+    for s in range(steps):
+        dr = synth.drags(dim_x, dim_y, s, n=12)
+        ctx.step_frame(dv, ca, cb, frame, dr, dim_x, dim_y, DT, 1.0, iters, 1.96)
+        ca, cb = cb, ca
+        ov, oc = oracle.step(ov, oc, dr, DT, 1.0, iters, 1.96)
+        assert_bit_equal(to_host(frame, np.uint16), oracle.upscale4_rgb565(oc), f"frame after step {s}")
+    assert_bit_equal(to_host(dv), ov, "v")
+    assert_bit_equal(to_host(ca, np.uint32), oc, "c")
+
+
+def test_upscale_into_an_unaligned_frame(ctx, oracle):
+    """fs_upscale4_rgb565 into a frame that is only 2-byte aligned (a uint16_t* inside a larger buffer)."""
+    dim_x, dim_y = 33, 17
+    _, c = rand_fields(32, dim_x, dim_y, 1.0)
+    n = 16 * (dim_x - 1) * (dim_y - 1)
+    buf = torch.zeros(n + 8, dtype=torch.int16, device="cuda")
+    for off in (1, 2, 3):
+        ctx.upscale4_rgb565(buf[off:off + n], to_dev(c), dim_x, dim_y)
+        assert_bit_equal(to_host(buf[off:off + n], np.uint16).reshape((dim_x - 1) * 4, (dim_y - 1) * 4),
+                         oracle.upscale4_rgb565(c), f"offset {off}")
