@@ -14,7 +14,7 @@ __all__ = ["LIB_PATH", "build_cuda", "build_harness", "Context", "Tile", "FluidE
 
 def __getattr__(name):
     # lazy: `import esp32_fluid_simulation_b200` must work before the library is built
-    if name in ("Context", "advect", "calculate_divergence", "subtract_gradient", "poisson_solve",
+    if name in ("Context", "Sim", "advect", "calculate_divergence", "subtract_gradient", "poisson_solve",
                 "DRAG_DTYPE", "default_context"):
         from . import ops
         return getattr(ops, name)

@@ -20,6 +20,7 @@ FS_ERR_NO_CONTEXT = -2
 FS_ERR_UNSUPPORTED = -3
 FS_ERR_HALO_OVERRUN = -4
 FS_ERR_HALO_TIMEOUT = -5
+FS_ERR_WOULD_BLOCK = -6
 
 
 class HaloCopy(C.Structure):
@@ -112,6 +113,14 @@ def lib() -> C.CDLL:
         "fs_ipc_close": ([vp, vp], I),
         "fs_halo_exchange": ([C.POINTER(HaloCopy), I, C.POINTER(vp), C.POINTER(vp), I, C.c_ulonglong, vp], I),
         "fs_ctx_set_stream": ([vp, vp], I),
+        "fs_sim_create": ([C.POINTER(vp), I, I, f, f, I, f, I, vp], I),
+        "fs_sim_destroy": ([vp], I),
+        "fs_sim_upload": ([vp, vp, vp], I),
+        "fs_sim_download": ([vp, vp, vp, vp, vp], I),
+        "fs_sim_step": ([vp, vp, I], I),
+        "fs_sim_acquire_frame": ([vp, C.POINTER(vp), C.POINTER(I), C.POINTER(I)], I),
+        "fs_sim_release_frame": ([vp], I),
+        "fs_sim_stats": ([vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)], I),
         "fs_dist_create": ([C.POINTER(vp), C.POINTER(DistConfig), vp], I),
         "fs_dist_destroy": ([vp], I),
         "fs_dist_window": ([vp, TP], I),

@@ -540,16 +540,20 @@ int launch_advect_rgb_tma(const Launch &L, uint32_t *next_c, const uint32_t *c, 
     return launch_tma<RgbPayload>(L, next_c, c, vel, g, dt, no_slip, status);
 }
 
-int launch_advect_div_tma(const Launch &L, float2 *v_out, const float2 *v_in, float *div, const fs_drag *drags_host,
-                          int n_drags, const Geo &g, float dt, float dx, const int *store_rect, int *status)
+// everything a launch of advect_div_tma_kernel passes: also what a CUDA-graph kernel node of it is re-armed with
+struct AdvDivLaunchParams {
+    CUtensorMap map;
+    AdvDivArgs args;
+    void *ptrs[2];
+};
+
+static int fill_advect_div(AdvDivLaunchParams &q, float2 *v_out, const float2 *v_in, float *div, const fs_drag *drags_host,
+                           int n_drags, const Geo &g, float dt, float dx, const int *store_rect, int *status)
 {
-    const int w = g.x1 - g.x0, h = g.y1 - g.y0;
-    if (w <= 0 || h <= 0) return 0;
     if (n_drags > AD_MAX_DRAGS) return (int)cudaErrorInvalidValue;
-    CUtensorMap in_map;
-    if (!tma_make_map_2d(&in_map, v_in, (uint64_t)g.nx * 2, g.ny, (uint64_t)g.nx * 2, AD_W * 2, AD_H))
+    if (!tma_make_map_2d(&q.map, v_in, (uint64_t)g.nx * 2, g.ny, (uint64_t)g.nx * 2, AD_W * 2, AD_H))
         return (int)cudaErrorInvalidValue;
-    AdvDivArgs a;
+    AdvDivArgs &a = q.args;
     a.v_out = v_out; a.v_in = v_in; a.div = div; a.g = g; a.dt = dt;
     a.sx0 = store_rect ? store_rect[0] : g.x0; a.sy0 = store_rect ? store_rect[1] : g.y0;
     a.sx1 = store_rect ? store_rect[2] : g.x1; a.sy1 = store_rect ? store_rect[3] : g.y1;
@@ -557,14 +561,42 @@ int launch_advect_div_tma(const Launch &L, float2 *v_out, const float2 *v_in, fl
     a.two_dx_inv = 1.0f / (2.0f * dx);
     a.n_drags = n_drags;
     for (int k = 0; k < n_drags; k++) a.drags[k] = drags_host[k];
+    q.ptrs[0] = &q.map;
+    q.ptrs[1] = &q.args;
+    return 0;
+}
+
+int launch_advect_div_tma(const Launch &L, float2 *v_out, const float2 *v_in, float *div, const fs_drag *drags_host,
+                          int n_drags, const Geo &g, float dt, float dx, const int *store_rect, int *status)
+{
+    const int w = g.x1 - g.x0, h = g.y1 - g.y0;
+    if (w <= 0 || h <= 0) return 0;
+    AdvDivLaunchParams q;
+    int e0 = fill_advect_div(q, v_out, v_in, div, drags_host, n_drags, g, dt, dx, store_rect, status);
+    if (e0) return e0;
     const size_t smem = ((AD_W * 2 * AD_H * 4 + 127) & ~127) + AD_AW * AD_AH * 8;
     cudaError_t e = cudaFuncSetAttribute(advect_div_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((w + AT_TX - 1) / AT_TX, (h + AT_TY - 1) / AT_TY);
-    advect_div_tma_kernel<<<grid, AT_THREADS, smem, L.stream>>>(in_map, a);
+    advect_div_tma_kernel<<<grid, AT_THREADS, smem, L.stream>>>(q.map, q.args);
     ++*L.launches;
     return (int)cudaGetLastError();
+}
+
+// ---- CUDA-graph support: the step's only per-step kernel arguments are the drag records of this kernel ----
+const void *advect_div_kernel_func() { return (const void *)advect_div_tma_kernel; }
+size_t advect_div_params_bytes() { return sizeof(AdvDivLaunchParams); }
+// fills `storage` (advect_div_params_bytes() bytes, must stay alive until the graph launch has been enqueued)
+// and returns the kernelParams array for cudaGraphExecKernelNodeSetParams
+int advect_div_graph_params(void *storage, void ***kernel_params, float2 *v_out, const float2 *v_in, float *div,
+                            const fs_drag *drags_host, int n_drags, const Geo &g, float dt, float dx)
+{
+    AdvDivLaunchParams *q = reinterpret_cast<AdvDivLaunchParams *>(storage);
+    int e = fill_advect_div(*q, v_out, v_in, div, drags_host, n_drags, g, dt, dx, nullptr, nullptr);
+    if (e) return e;
+    *kernel_params = q->ptrs;
+    return 0;
 }
 
 int advect_div_max_drags() { return AD_MAX_DRAGS; }

@@ -159,6 +159,7 @@ const char *fs_error_string(int code)
         case FS_ERR_UNSUPPORTED: return "unsupported";
         case FS_ERR_HALO_OVERRUN: return "advect backtrace left the local window";
         case FS_ERR_HALO_TIMEOUT: return "halo exchange: a neighbour never signalled";
+        case FS_ERR_WOULD_BLOCK: return "would block: frame slots full / no frame produced";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
     }
 }

@@ -35,6 +35,11 @@ int launch_advect_div_tma(const Launch &L, float2 *v_out, const float2 *v_in, fl
                           int n_drags, const Geo &g, float dt, float dx, const int *store_rect = nullptr,
                           int *status = nullptr);
 int advect_div_max_drags();
+// CUDA-graph support (sim.cu): re-arm a captured advect_div_tma_kernel node with a step's drag records
+const void *advect_div_kernel_func();
+size_t advect_div_params_bytes();
+int advect_div_graph_params(void *storage, void ***kernel_params, float2 *v_out, const float2 *v_in, float *div,
+                            const fs_drag *drags_host, int n_drags, const Geo &g, float dt, float dx);
 // fused dye advect + 4x RGB565 frame of the advected dye (ino:282 + ino:116-177): the frame covers the
 // cells that start at the nodes of g's compute rectangle (needs the dye valid one node beyond the
 // advect halo); frame = first pixel of the cell at (x0, y0), frame_cells_y = its cell columns

@@ -365,6 +365,70 @@ class Context:
         check(self._L.fs_ctx_set_stream(self._h, C.c_void_p(s)), "fs_ctx_set_stream")
 
 
+class Sim:
+    """fs_sim: a device-resident simulation stepped by one CUDA-graph launch per loop() body, with the sketch's
+    colour hand-off (ino:285-288) as a double-buffered asynchronous frame stream into pinned host memory."""
+
+    def __init__(self, ctx: Context, dim_x: int, dim_y: int, dt, dx, iters: int, omega, frame: bool = False):
+        self.ctx, self._L = ctx, ctx._L
+        self.dim_x, self.dim_y = dim_x, dim_y
+        h = C.c_void_p()
+        check(self._L.fs_sim_create(C.byref(h), dim_x, dim_y, dt, dx, iters, omega, int(bool(frame)), ctx._h), "fs_sim_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            if getattr(self.ctx, "_h", None):
+                self._L.fs_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def upload(self, v, c):
+        check(self._L.fs_sim_upload(self._h, _ptr(v, "float32")[0], _ptr(c, "uint32")[0]), "fs_sim_upload")
+
+    def download(self):
+        n = self.dim_x * self.dim_y
+        v = np.empty((self.dim_y, self.dim_x, 2), np.float32)
+        c = np.empty((self.dim_y, self.dim_x, 3), np.uint32)
+        p, d = np.empty((self.dim_y, self.dim_x), np.float32), np.empty((self.dim_y, self.dim_x), np.float32)
+        check(self._L.fs_sim_download(self._h, v.ctypes.data, c.ctypes.data, p.ctypes.data, d.ctypes.data), "fs_sim_download")
+        assert v.size == 2 * n
+        return v, c, p, d
+
+    def step(self, drags=None) -> bool:
+        """False when both frame slots still wait for the consumer (FS_ERR_WOULD_BLOCK); True after a step."""
+        d, nd = _drags(drags)
+        code = self._L.fs_sim_step(self._h, d.ctypes.data if nd else None, nd)
+        if code == _lib.FS_ERR_WOULD_BLOCK:
+            return False
+        check(code, "fs_sim_step")
+        return True
+
+    def acquire_frame(self):
+        """The oldest unconsumed frame as a numpy VIEW of the pinned host buffer (valid until release_frame), or None."""
+        ptr, rows, cols = C.c_void_p(), C.c_int(), C.c_int()
+        code = self._L.fs_sim_acquire_frame(self._h, C.byref(ptr), C.byref(rows), C.byref(cols))
+        if code == _lib.FS_ERR_WOULD_BLOCK:
+            return None
+        check(code, "fs_sim_acquire_frame")
+        buf = (C.c_uint16 * (rows.value * cols.value)).from_address(ptr.value)
+        return np.frombuffer(buf, np.uint16).reshape(rows.value, cols.value)
+
+    def release_frame(self):
+        check(self._L.fs_sim_release_frame(self._h), "fs_sim_release_frame")
+
+    @property
+    def stats(self) -> dict:
+        a, b, c = C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong()
+        check(self._L.fs_sim_stats(self._h, C.byref(a), C.byref(b), C.byref(c)), "fs_sim_stats")
+        return {"steps": a.value, "graph_launches": b.value, "eager_steps": c.value}
+
+
 # ---- module-level functions with the reference's exact names -------------------------
 _default_ctx: dict[int, Context] = {}
 

@@ -43,6 +43,7 @@ extern "C" {
 #define FS_ERR_NO_CONTEXT (-2)
 #define FS_ERR_UNSUPPORTED (-3)
 #define FS_ERR_HALO_OVERRUN (-4)  /* decomposed advect: backtrace left the local window */
+#define FS_ERR_WOULD_BLOCK (-6)   /* fs_sim: both frame slots wait for the consumer / no frame produced yet */
 #define FS_ERR_HALO_TIMEOUT (-5)  /* fs_halo_exchange: a neighbour never signalled (see "halo_timeout_ms") */
 /* positive values are cudaError_t codes */
 
@@ -272,6 +273,30 @@ int fs_halo_exchange(const fs_halo_copy *copies, int n_copies, void *const *sign
 /* Re-target the context at another stream (e.g. a capturing stream). */
 int fs_ctx_set_stream(fs_ctx *ctx, void *stream);
 
+
+/* ---- a device-resident simulation: one CUDA-graph launch per step + an asynchronous frame stream -----
+ * (SURVEY.md §8f #2).  The sketch's loop() task hands every step's dye to the draw task through the
+ * color_consumed / color_produced semaphore pair (ino:285-288) — a double buffer.  fs_sim keeps the
+ * state on the device, runs a step as ONE cudaGraphLaunch (the per-step drag records are written into
+ * the captured kernel node with cudaGraphExecKernelNodeSetParams; two graphs stand for the dye pointer
+ * swap of ino:286), renders the step's RGB565 frame inside the dye advect (frame = 1) and streams it
+ * to one of two pinned host buffers on a copy stream while the next step computes.
+ *   producer: fs_sim_step        (FS_ERR_WOULD_BLOCK when two frames are waiting for the consumer)
+ *   consumer: fs_sim_acquire_frame (waits for the oldest frame's copy; "take color_produced")
+ *             fs_sim_release_frame ("give color_consumed")
+ * Small or odd-pitched grids that the fused kernels cannot take are stepped without a graph; results
+ * are identical either way. */
+typedef struct fs_sim fs_sim;
+int fs_sim_create(fs_sim **out, int dim_x, int dim_y, float dt, float dx, int iters, float omega, int frame,
+                  fs_ctx *ctx);
+int fs_sim_destroy(fs_sim *s);
+int fs_sim_upload(fs_sim *s, const fs_vec2f *v, const fs_rgb_uq32 *c);                 /* host or device pointers */
+int fs_sim_download(fs_sim *s, fs_vec2f *v, fs_rgb_uq32 *c, float *p, float *div);     /* any may be NULL; synchronises */
+int fs_sim_step(fs_sim *s, const fs_drag *drags, int n_drags);                         /* `drags`: HOST array */
+int fs_sim_acquire_frame(fs_sim *s, const uint16_t **frame, int *rows, int *cols);     /* pinned host memory */
+int fs_sim_release_frame(fs_sim *s);
+int fs_sim_stats(const fs_sim *s, unsigned long long *steps, unsigned long long *graph_launches,
+                 unsigned long long *eager_steps);
 
 /* ---- the decomposed step as ONE object per rank (fs_dist_*) -----------------------
  * fs_dist owns a rank's windows of every field (one IPC-exportable arena), knows its neighbours and

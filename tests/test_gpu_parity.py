@@ -527,3 +527,90 @@ def test_upscale_into_an_unaligned_frame(ctx, oracle):
         ctx.upscale4_rgb565(buf[off:off + n], to_dev(c), dim_x, dim_y)
         assert_bit_equal(to_host(buf[off:off + n], np.uint16).reshape((dim_x - 1) * 4, (dim_y - 1) * 4),
                          oracle.upscale4_rgb565(c), f"offset {off}")
+
+
+# ---- f2: one CUDA-graph launch per step + the asynchronous frame stream (ino:285-288) -------------------
+
+def test_sim_graph_steps_match_oracle(oracle):
+    """fs_sim: after two eager steps the step is ONE graph launch whose drag records are re-armed per step."""
+    import esp32_fluid_simulation_b200 as fb
+    from esp32_fluid_simulation_b200 import synth
+    dim_x, dim_y, iters, steps = 256, 192, 20, 9
+    ctx = fb.Context(0, torch.cuda.Stream())
+    sim = fb.Sim(ctx, dim_x, dim_y, DT, 1.0, iters, 1.96)
+    v, c = synth.velocity(dim_x, dim_y, vmax=90.0), synth.dye(dim_x, dim_y)
+    sim.upload(v, c)
+    launches0 = ctx.launch_count
+    ov, oc = v.copy(), c.copy()
+    for s in range(steps):
+        dr = synth.drags(dim_x, dim_y, s, n=(s * 5) % 17)          # a different number of records every step, 0 included
+        assert sim.step(dr)
+        ov, oc, op, od = oracle.step(ov, oc, dr, DT, 1.0, iters, 1.96, want_fields=True)
+    gv, gc, gp, gd = sim.download()
+    assert_bit_equal(gv, ov, "v")
+    assert_bit_equal(gc, oc, "c")
+    assert_bit_equal(gp, op, "p")
+    assert_bit_equal(gd, od, "d")
+    st = sim.stats
+    assert st["steps"] == steps and st["graph_launches"] == steps - 2 and st["eager_steps"] == 2, st
+    per_step = (ctx.launch_count - launches0) / steps
+    assert per_step == int(per_step) and per_step >= 4, per_step     # kernels per step are still counted
+    sim.close()
+
+
+def test_sim_small_grid_steps_without_a_graph(oracle):
+    import esp32_fluid_simulation_b200 as fb
+    from esp32_fluid_simulation_b200 import synth
+    ctx = fb.Context(0)
+    sim = fb.Sim(ctx, 61, 81, DT, 1.0, 10, 1.96)
+    v, c = synth.velocity(61, 81, vmax=90.0), synth.dye(61, 81)
+    sim.upload(v, c)
+    ov, oc = v.copy(), c.copy()
+    for s in range(5):
+        dr = synth.drags(61, 81, s, n=4)
+        assert sim.step(dr)
+        ov, oc = oracle.step(ov, oc, dr, DT, 1.0, 10, 1.96)
+    gv, gc, _, _ = sim.download()
+    assert_bit_equal(gv, ov, "v")
+    assert_bit_equal(gc, oc, "c")
+    assert sim.stats["graph_launches"] == 0
+    sim.close()
+
+
+def test_sim_frame_stream_is_a_double_buffer(oracle):
+    """The colour hand-off of ino:285-288: the producer may be two frames ahead, then it must wait for the consumer;
+    frames arrive in order in pinned host memory and equal draw_routine() of the reference on each step's dye."""
+    import esp32_fluid_simulation_b200 as fb
+    from esp32_fluid_simulation_b200 import synth
+    dim_x, dim_y, iters = 192, 128, 12
+    ctx = fb.Context(0, torch.cuda.Stream())
+    sim = fb.Sim(ctx, dim_x, dim_y, DT, 1.0, iters, 1.96, frame=True)
+    v, c = synth.velocity(dim_x, dim_y, vmax=90.0), synth.dye(dim_x, dim_y)
+    sim.upload(v, c)
+    assert sim.acquire_frame() is None                               # nothing produced yet
+    ov, oc = v.copy(), c.copy()
+    want = []
+    produced = consumed = 0
+    for s in range(8):
+        dr = synth.drags(dim_x, dim_y, s, n=6)
+        if not sim.step(dr):                                         # both slots full: consume one, then the step goes through
+            assert produced - consumed == 2
+            f = sim.acquire_frame()
+            assert_bit_equal(f, want[consumed], f"frame {consumed}")
+            sim.release_frame()
+            consumed += 1
+            assert sim.step(dr)
+        produced += 1
+        ov, oc = oracle.step(ov, oc, dr, DT, 1.0, iters, 1.96)
+        want.append(oracle.upscale4_rgb565(oc))
+    while consumed < produced:
+        f = sim.acquire_frame()
+        assert_bit_equal(f, want[consumed], f"frame {consumed}")
+        sim.release_frame()
+        consumed += 1
+    assert sim.acquire_frame() is None
+    gv, gc, _, _ = sim.download()
+    assert_bit_equal(gv, ov, "v")
+    assert_bit_equal(gc, oc, "c")
+    assert sim.stats["graph_launches"] >= 4
+    sim.close()
