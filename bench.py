@@ -299,12 +299,14 @@ def run_b200_arm(args):
 
 
 def bench_single(args, fb, synth, torch):
-    n = GRID
-    nodes = n * n
+    n, ny = GRID, GRID
+    if getattr(args, "grid", ""):        # denominators for the decomposed configs: one rank's rectangle on one GPU
+        n, ny = (int(t) for t in args.grid.lower().split("x"))
+    nodes = n * ny
     stream = torch.cuda.Stream()
     ctx = fb.Context(0, stream)
-    v0, c0 = synth.velocity(n, n), synth.dye(n, n)
-    drags = [synth.drags(n, n, s, n=N_DRAGS) for s in range(args.warmup + args.steps)]
+    v0, c0 = synth.velocity(n, ny), synth.dye(n, ny)
+    drags = [synth.drags(n, ny, s, n=N_DRAGS) for s in range(args.warmup + args.steps)]
     with torch.cuda.stream(stream):
         dv = torch.from_numpy(v0).cuda()
         dc = torch.from_numpy(c0.view(np.int32)).cuda()
@@ -316,7 +318,7 @@ def bench_single(args, fb, synth, torch):
 
     def step(s):
         # loop() swaps the dye pointers (ino:286): c_in -> c_out, then the roles alternate
-        ctx.step_pingpong(dv, dyes[s & 1], dyes[(s & 1) ^ 1], drags[s], n, n, synth.DT, synth.DX, ITERS, synth.OMEGA)
+        ctx.step_pingpong(dv, dyes[s & 1], dyes[(s & 1) ^ 1], drags[s], n, ny, synth.DT, synth.DX, ITERS, synth.OMEGA)
 
     for s in range(args.warmup):
         step(s)
@@ -343,16 +345,16 @@ def bench_single(args, fb, synth, torch):
 
     # --- dominant kernel: the SOR solve, timed alone on the same stream ---
     with torch.cuda.stream(stream):
-        dd = torch.randn(n, n, device="cuda") * 10
+        dd = torch.randn(ny, n, device="cuda") * 10
         dp = torch.empty_like(dd)
     for _ in range(2):
-        ctx.poisson_solve(dp, dd, n, n, synth.DX, ITERS, synth.OMEGA)
+        ctx.poisson_solve(dp, dd, n, ny, synth.DX, ITERS, synth.OMEGA)
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 5
     l0 = ctx.launch_count
     s0.record(stream)
     for _ in range(reps):
-        ctx.poisson_solve(dp, dd, n, n, synth.DX, ITERS, synth.OMEGA)
+        ctx.poisson_solve(dp, dd, n, ny, synth.DX, ITERS, synth.OMEGA)
     s1.record(stream)
     stream.synchronize()
     sor_launches = (ctx.launch_count - l0) // reps
@@ -368,7 +370,7 @@ def bench_single(args, fb, synth, torch):
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            if tj.get("sor_t") == sor_t and tj.get("sor_shape") == sor_shape and tj.get("grid") == [n, n]:
+            if tj.get("sor_t") == sor_t and tj.get("sor_shape") == sor_shape and tj.get("grid") == [n, ny]:
                 traffic, traffic_solve = tj.get("dram_bytes_per_pass"), tj.get("dram_bytes_per_solve")
                 traffic_src = tj.get("source")
         except Exception:
@@ -408,11 +410,11 @@ def bench_single(args, fb, synth, torch):
     adv = {}
     for name, bpn, fn in (
             ("advect velocity + drags + divergence (advect_div_tma_kernel, fused in fs_step)", 28.0,
-             lambda: ctx.advect_drags_divergence(dv2, dd, dv, drags[0], n, n, synth.DT, synth.DX)),
+             lambda: ctx.advect_drags_divergence(dv2, dd, dv, drags[0], n, ny, synth.DT, synth.DX)),
             ("advect velocity (advect_tma_kernel<Vec2Payload>)", 16.0,
-             lambda: ctx.advect(dv2, dv, dv, n, n, synth.DT, True)),
+             lambda: ctx.advect(dv2, dv, dv, n, ny, synth.DT, True)),
             ("advect dye (advect_tma_kernel<RgbPayload>)", 32.0,
-             lambda: ctx.advect(dc2, dc, dv, n, n, synth.DT, False))):
+             lambda: ctx.advect(dc2, dc, dv, n, ny, synth.DT, False))):
         t_ms = timed(fn)
         gbs = bpn * nodes / (t_ms * 1e-3) / 1e9
         adv[name] = {"ms": t_ms, "algorithmic_bytes_per_node": bpn, "achieved": gbs, "unit": "GB/s", "frac": gbs / peak}
@@ -445,16 +447,65 @@ def bench_single(args, fb, synth, torch):
     except Exception as e:  # noqa: BLE001 — never let an extra take the headline down
         extra["ensemble"] = {"error": f"{type(e).__name__}: {e}"}
 
+    # --- fs_sim: the same step as ONE CUDA-graph launch, and the frame-only end-to-end path ---
+    try:
+        sim = fb.Sim(ctx, n, ny, synth.DT, synth.DX, ITERS, synth.OMEGA)
+        sim.upload(dv, dc)
+        for s in range(4):
+            sim.step(drags[s % len(drags)])
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k_steps = max(args.steps, 10)
+        l0 = ctx.launch_count
+        g0.record(stream)
+        for s in range(k_steps):
+            sim.step(drags[s % len(drags)])
+        g1.record(stream)
+        stream.synchronize()
+        st = sim.stats
+        extra["graph_step"] = {"ms_per_step": g0.elapsed_time(g1) / k_steps, "graph_launches_per_step": 1,
+                               "kernels_per_graph": (ctx.launch_count - l0) // k_steps, "stats": st,
+                               "api": "fs_sim_step: one cudaGraphLaunch per loop() body, drag records re-armed with "
+                                      "cudaGraphExecKernelNodeSetParams"}
+        sim.close()
+        # frames only leave the device: state resident, every step's 4x RGB565 frame streamed to pinned host memory
+        simf = fb.Sim(ctx, n, ny, synth.DT, synth.DX, ITERS, synth.OMEGA, frame=True)
+        simf.upload(dv, dc)
+        f_steps, got = 6, 0
+        for s in range(2):                       # warm-up: two eager steps, then the graphs exist
+            simf.step(drags[s])
+        while simf.acquire_frame() is not None:
+            simf.release_frame()
+        t0 = time.perf_counter()
+        for s in range(f_steps):
+            while not simf.step(drags[s % len(drags)]):
+                simf.acquire_frame()
+                simf.release_frame()
+                got += 1
+        while got < f_steps:
+            simf.acquire_frame()
+            simf.release_frame()
+            got += 1
+        f_s = (time.perf_counter() - t0) / f_steps
+        frame_bytes = 16 * (n - 1) * (ny - 1) * 2
+        extra["e2e_frames_only"] = {"value": nodes / f_s / 1e6, "unit": UNIT, "ms_per_step": f_s * 1e3, "steps": f_steps,
+                                    "h2d_bytes_per_step": 12 * N_DRAGS, "d2h_bytes_per_step": frame_bytes,
+                                    "api": "fs_sim_step + fs_sim_acquire_frame/release_frame: state stays on the device, "
+                                           "the step's RGB565 frame (rendered inside the dye advect) is copied to pinned "
+                                           "host memory on a side stream under the next step (PCIe-bound: 32 B/node)"}
+        simf.close()
+    except Exception as e:  # noqa: BLE001
+        extra["graph_step"] = {"error": f"{type(e).__name__}: {e}"}
+
     # --- e2e: the host-pointer drop-in fsh_step with pinned host buffers ---
     hv = torch.from_numpy(v0.copy()).pin_memory()
     hc = torch.from_numpy(c0.view(np.int32).copy()).pin_memory()
     hv_np, hc_np = hv.numpy(), hc.numpy().view(np.uint32)
     e2e_steps = max(3, min(args.steps, 10))
     for s in range(2):
-        ctx.step(hv_np, hc_np, drags[s % len(drags)], n, n, synth.DT, synth.DX, ITERS, synth.OMEGA)
+        ctx.step(hv_np, hc_np, drags[s % len(drags)], n, ny, synth.DT, synth.DX, ITERS, synth.OMEGA)
     t0 = time.perf_counter()
     for s in range(e2e_steps):
-        ctx.step(hv_np, hc_np, drags[s % len(drags)], n, n, synth.DT, synth.DX, ITERS, synth.OMEGA)
+        ctx.step(hv_np, hc_np, drags[s % len(drags)], n, ny, synth.DT, synth.DX, ITERS, synth.OMEGA)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     state_bytes = nodes * (8 + 12)
     e2e = {"value": nodes / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": state_bytes + 12 * N_DRAGS,
@@ -463,7 +514,7 @@ def bench_single(args, fb, synth, torch):
 
     # --- cpu baseline beside it (bounded: 2 full-size steps, ~12 s) ---
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and n == ny == GRID:
         rate, sec, kind = cpu_step_rate(n, n, 2, 0)
         cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind,
                "sample": f"2 full steps of the same {n}x{n} K={ITERS} workload, single thread "
@@ -473,8 +524,8 @@ def bench_single(args, fb, synth, torch):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32+uq32", "data": "synthetic",
-        "config": {"workload": f"single {n}x{n} grid, {ITERS} SOR iterations, velocity + dye advection",
-                   "grid": [n, n], "sor_iters": ITERS, "drags_per_step": N_DRAGS,
+        "config": {"workload": f"single {n}x{ny} grid, {ITERS} SOR iterations, velocity + dye advection",
+                   "grid": [n, ny], "sor_iters": ITERS, "drags_per_step": N_DRAGS,
                    "l2": "state (v 134 MB + dye 201 MB + p/div 134 MB) exceeds the 126 MB L2; no flush needed",
                    "options": {k: ctx.get_option(k) for k in ("sor", "sor_t", "sor_shape", "advect", "fuse")}},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
@@ -489,6 +540,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grid", default="", help="N=1 only: WxH grid instead of 4096x4096 (the single-GPU denominator of a "
+                    "decomposed config, e.g. 8192x4096 = one rank's rectangle of 16384^2 on 8 GPUs)")
     ap.add_argument("--global-grid", default="", help="N>1 only: GXxGY global grid instead of 4096^2 per GPU "
                     "(BASELINE.json configs[3] = 16384x16384, configs[4] = 24576x32768)")
     ap.add_argument("--iters", type=int, default=ITERS, help="SOR iterations per step (N>1 extra configs)")
