@@ -45,7 +45,7 @@ class DistInfo(C.Structure):
     """fs_dist_info_t"""
     _fields_ = [(n, C.c_int) for n in ("px", "py", "n_neighbours", "sor_passes", "sor_t", "div_ring",
                                       "velocity_halo", "dye_halo", "exchanges_per_step")] + \
-               [("exchanges", C.c_ulonglong), ("arena_bytes", C.c_size_t)]
+               [("exchanges", C.c_ulonglong), ("arena_bytes", C.c_size_t), ("phase_ms", C.c_float * 5)]
 
 
 _lib = None

@@ -91,6 +91,8 @@ struct fs_dist {
     int has_l, has_r, has_d, has_u;
     uint16_t *frame;                   // this rank's part of the RGB565 frame (cfg.frame), or nullptr
     int cells_x, cells_y;
+    cudaEvent_t ev[6];                 // phase boundaries of the LAST step (fs_dist_info: phase_ms)
+    bool ev_valid;
 };
 
 namespace {
@@ -302,6 +304,8 @@ int fs_dist_create(fs_dist **out, const fs_dist_config *cfg, fs_ctx *ctx)
             return (int)e;
         }
     }
+    for (int k = 0; k < 6; k++) cudaEventCreate(&d->ev[k]);
+    d->ev_valid = false;
     d->cur_v = d->cur_c = 0;
     d->connected = d->n_nb == 0;
     d->seq = 0;
@@ -321,6 +325,7 @@ int fs_dist_destroy(fs_dist *d)
         if (d->nb[k].opened) cudaIpcCloseMemHandle(d->nb[k].base);
     cudaFree(d->arena);
     cudaFree(d->frame);
+    for (int k = 0; k < 6; k++) cudaEventDestroy(d->ev[k]);
     delete d;
     return FS_OK;
 }
@@ -357,6 +362,11 @@ int fs_dist_info(const fs_dist *d, fs_dist_info_t *info)
     info->exchanges_per_step = d->n_nb ? (d->n_pass > 0 ? d->n_pass : 1) : 0;
     info->exchanges = d->exchanges;
     info->arena_bytes = d->arena_bytes;
+    // phases of the last step (CUDA events on the compute stream): advect+drags+div | SOR passes (with their fused
+    // exchanges) | gradient | velocity+dye exchange | dye advect (+frame)
+    for (int k = 0; k < 5; k++) info->phase_ms[k] = -1.0f;
+    if (d->ev_valid && cudaEventSynchronize(d->ev[5]) == cudaSuccess)
+        for (int k = 0; k < 5; k++) cudaEventElapsedTime(&info->phase_ms[k], d->ev[k], d->ev[k + 1]);
     return FS_OK;
 }
 
@@ -464,6 +474,7 @@ int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags)
         if ((e = exchange_fields(d, offs, es, ws, 1))) return e;
     }
     d->v_halo_ok = true;
+    cudaEventRecord(d->ev[0], ctx->stream);
 
     // ---- 1. advect v (no-slip) + drags + divergence (ino:253, 264-269, 274) -------------------------
     Geo gd = gw;                                   // divergence rectangle: owned, grown by D
@@ -490,6 +501,7 @@ int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags)
         v_forced = (const fs_vec2f *)scratch;
     }
 
+    cudaEventRecord(d->ev[1], ctx->stream);
     // ---- 2. SOR (ino:275): P blocked passes, each fused with its halo exchange ---------------------------
     float *bufs[2] = {field<float>(d, d->off_p[0]), field<float>(d, d->off_p[1])};
     if (d->n_pass == 0) {
@@ -544,9 +556,11 @@ int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags)
         d->p_last = bufs[(d->n_pass - 1) & 1];
     }
 
+    cudaEventRecord(d->ev[2], ctx->stream);
     // ---- 3. gradient-subtract (ino:276) on the rectangle: v2 = v_forced - grad p ---------------------------------
     if ((e = launch_subtract_gradient(mk(ctx), (float2 *)v2, (const float2 *)v_forced, d->p_last, gw, cfg.dx))) return e;
 
+    cudaEventRecord(d->ev[3], ctx->stream);
     // ---- 4. projected velocity + dye halos in ONE exchange kernel --------------------------------------------
     if (multi) {
         const size_t offs[2] = {d->off_v[d->cur_v ^ 1], d->off_c[d->cur_c]};
@@ -554,6 +568,7 @@ int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags)
         if ((e = exchange_fields(d, offs, es, ws, d->cw > 0 ? 2 : 1))) return e;
     }
 
+    cudaEventRecord(d->ev[4], ctx->stream);
     // ---- 5. advect dye (ino:282, free-slip sampling) with the projected velocity -------------------------------
     Geo gc = gw;
     grow_rect(gw, d->cw, gc.vx0, gc.vy0, gc.vx1, gc.vy1);   // dye ghosts are valid to width cw
@@ -566,6 +581,8 @@ int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags)
         return e;
     }
 
+    cudaEventRecord(d->ev[5], ctx->stream);
+    d->ev_valid = true;
     d->cur_v ^= 1;    // ino:255 / ino:286: the pointer swaps
     d->cur_c ^= 1;
     return FS_OK;

@@ -39,15 +39,28 @@ halo_exchange_kernel(const HaloArgs a, unsigned int *done_counter, int *status)
         const int b0 = c == 0 ? 0 : a.block_end[c - 1];
         const int nb = a.block_end[c] - b0, b = blockIdx.x - b0;
         if (d.vec16) {
-            // 16-byte path (rows, pitches and bases are 16-byte multiples: the usual case)
-            const int row_q = d.row_words >> 2;
-            const long long quads = (long long)row_q * d.rows;
+            // 16-byte path (rows, pitches and bases are 16-byte multiples: the usual case), four independent
+            // load/store pairs in flight per thread — peer stores over NVLink are latency-bound otherwise
+            // (round 2: 160 GB/s with one pair per thread)
+            const unsigned row_q = (unsigned)(d.row_words >> 2);
+            const unsigned quads = row_q * (unsigned)d.rows;
             const uint4 *src = reinterpret_cast<const uint4 *>(d.src);
             uint4 *dst = reinterpret_cast<uint4 *>(d.dst);
             const size_t sp = d.src_pitch_words >> 2, dp = d.dst_pitch_words >> 2;
-            for (long long k = (long long)b * blockDim.x + threadIdx.x; k < quads; k += (long long)nb * blockDim.x) {
-                const int r = (int)(k / row_q), w = (int)(k - (long long)r * row_q);
-                dst[(size_t)r * dp + w] = __ldg(src + (size_t)r * sp + w);
+            const unsigned stride = (unsigned)nb * blockDim.x;
+            for (unsigned k0 = (unsigned)b * blockDim.x + threadIdx.x; k0 < quads; k0 += 4 * stride) {
+                uint4 val[4];
+                unsigned r[4], w[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const unsigned k = k0 + u * stride;
+                    r[u] = k / row_q;
+                    w[u] = k - r[u] * row_q;
+                    if (k < quads) val[u] = __ldg(src + (size_t)r[u] * sp + w[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (k0 + u * stride < quads) dst[(size_t)r[u] * dp + w[u]] = val[u];
             }
         } else {
             const long long words = (long long)d.row_words * d.rows;
@@ -89,17 +102,17 @@ int launch_halo_exchange(const Launch &L, HaloArgs &a, unsigned int *done_counte
 {
     if (a.n_copies < 0 || a.n_copies > HALO_MAX_COPIES || a.n_peers < 0 || a.n_peers > HALO_MAX_PEERS)
         return (int)cudaErrorInvalidValue;
-    // ~32 KB of payload per block, at least one block per copy, at most 4 per SM
+    // ~16 KB of payload per block, at least one block per copy, at most 8 per SM
     long long total = 0;
     for (int c = 0; c < a.n_copies; c++) total += (long long)a.copies[c].row_words * a.copies[c].rows * 4;
-    const int budget = L.num_sms * 4;
+    const int budget = L.num_sms * 8;
     int blocks = 0;
     for (int c = 0; c < a.n_copies; c++) {
         HaloCopy &h = a.copies[c];
         h.vec16 = ((h.row_words | h.src_pitch_words | h.dst_pitch_words) & 3) == 0 && (uintptr_t)h.src % 16 == 0 &&
                   (uintptr_t)h.dst % 16 == 0;
         const long long bytes = (long long)a.copies[c].row_words * a.copies[c].rows * 4;
-        long long nb = (bytes + 32767) / 32768;
+        long long nb = (bytes + 16383) / 16384;
         if (total > 0 && nb > 1) {
             const long long cap = (long long)budget * bytes / total + 1;
             if (nb > cap) nb = cap;

@@ -216,15 +216,18 @@ __device__ __forceinline__ unsigned long long halo_global_ns()
     return t;
 }
 
-// one thread: wait until every neighbour's flag carries `seq` (their strips are in our ghosts)
+// warp 0: wait until every neighbour's flag carries `seq` (their strips are in our ghosts).  Lane k polls
+// neighbour k's flag, so the system-scope acquire loads (~1-2 us each) overlap instead of queueing up
+// behind each other on one thread.
 __device__ __forceinline__ void wait_for_neighbours(const SorPushArgs &q)
 {
-    const unsigned long long t0 = halo_global_ns();
-    for (int k = 0; k < q.n_wait; k++) {
-        if (q.status && *reinterpret_cast<volatile int *>(q.status) == FS_ERR_HALO_TIMEOUT) break;   // already given up
+    const int lane = threadIdx.x & 31;
+    if (lane < q.n_wait) {
+        const unsigned long long t0 = halo_global_ns();
         for (;;) {
+            if (q.status && *reinterpret_cast<volatile int *>(q.status) == FS_ERR_HALO_TIMEOUT) break;   // already given up
             unsigned long long seen;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(q.wait[k]) : "memory");
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(q.wait[lane]) : "memory");
             if (seen >= q.seq_wait) break;
             if (q.timeout_ns && halo_global_ns() - t0 > q.timeout_ns) {
                 if (q.status) atomicExch(q.status, FS_ERR_HALO_TIMEOUT);
@@ -233,6 +236,7 @@ __device__ __forceinline__ void wait_for_neighbours(const SorPushArgs &q)
             __nanosleep(100);
         }
     }
+    __syncwarp();
     asm volatile("fence.proxy.async;" ::: "memory");   // the neighbours' generic stores -> this CTA's TMA reads
 }
 
@@ -375,31 +379,34 @@ __device__ __forceinline__ void sor_blocked_tma_body(const CUtensorMap &p_map, c
     // moment this CTA exits: their prologue and their first d load then overlap this pass's tail.
     if (a.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     int ahead = n_tiles;                       // thread 0 only: the ticket drawn one tile early
-    if (threadIdx.x == 0) {
+    if (w == 0) {
         // (the tile counters of all passes were zeroed before the solve's first pass)
-        const int first = atomicAdd(work_counter, 1);
-        s_tile[0] = first;
-        if (first < n_tiles && has_p) {
-            // (2) this grid may have been scheduled while the previous pass is still draining: d does
-            // not depend on it — load it now; p_in is its output and must wait
-            int tx, ty;
-            tile_coords(first, ntx, nty, tx, ty);
-            const int x = a.lax + tx * a.tw_out - a.hpx, y = a.lay + ty * a.th_out - a.hpy;
-            mbar_expect_tx(&bar, tx_bytes);
-            tma_load_2d(sd, &d_map, x, y, &bar);
-            asm volatile("griddepcontrol.wait;" ::: "memory");
-            if constexpr (PUSH) {
-                if (push->n_wait > 0) wait_for_neighbours(*push);   // p_in's ghosts are the neighbours' previous pass
+        int first = n_tiles, fx = 0, fy = 0;
+        if (t == 0) {
+            first = atomicAdd(work_counter, 1);
+            s_tile[0] = first;
+            if (first < n_tiles) {
+                int tx, ty;
+                tile_coords(first, ntx, nty, tx, ty);
+                fx = a.lax + tx * a.tw_out - a.hpx;
+                fy = a.lay + ty * a.th_out - a.hpy;
+                mbar_expect_tx(&bar, tx_bytes);
+                // (2) this grid may have been scheduled while the previous pass is still draining: d does
+                // not depend on it (pass >= 2) — load it now; p_in is the previous pass's output and must wait
+                if (has_p) tma_load_2d(sd, &d_map, fx, fy, &bar);
             }
-            tma_load_2d(sp, &p_map, x, y, &bar);
-        } else {
-            asm volatile("griddepcontrol.wait;" ::: "memory");      // pass 1: d is the previous KERNEL's output
-            if constexpr (PUSH) {
-                if (push->n_wait > 0) wait_for_neighbours(*push);
-            }
-            prefetch(first);
         }
-        ahead = atomicAdd(work_counter, 1);
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if constexpr (PUSH) {
+            if (push->n_wait > 0) wait_for_neighbours(*push);       // p_in's ghosts are the neighbours' previous pass
+        }
+        if (t == 0) {
+            if (first < n_tiles) {
+                if (has_p) tma_load_2d(sp, &p_map, fx, fy, &bar);
+                else       tma_load_2d(sd, &d_map, fx, fy, &bar);   // pass 1: d is the previous KERNEL's output
+            }
+            ahead = atomicAdd(work_counter, 1);
+        }
     }
     __syncthreads();
     uint32_t phase = 0;
@@ -455,14 +462,21 @@ __device__ __forceinline__ void sor_blocked_tma_body(const CUtensorMap &p_map, c
         if constexpr (PUSH) {
             if (push->n_peers > 0 && region_is_rim<R, NW>(g, *push, rlx0, rly0)) {
                 // publish: the CTA that completes the LAST rim tile tells every neighbour that this
-                // rank's strips are in their ghosts — interior tiles keep running underneath
-                __threadfence_system();
+                // rank's strips are in their ghosts — interior tiles keep running underneath.
+                // Ordering (PTX memory model, causality order is cumulative): this CTA's peer stores
+                // happen-before thread 0's acq_rel increment (bar.sync, then a gpu-scope release); the
+                // last incrementer acquires every earlier increment and then RELEASES the flags at
+                // system scope, so a neighbour that acquires a flag sees all rim tiles' stores.  No
+                // per-thread system fence: it stalled all 16 warps for microseconds on every rim tile.
                 __syncthreads();
-                if (threadIdx.x == 0 && atomicAdd(push->rim_done, 1) == push->rim_total - 1) {
-                    __threadfence_system();
-                    for (int k = 0; k < push->n_peers; k++)
-                        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(push->signal[k]), "l"(push->seq_signal)
-                                     : "memory");
+                if (threadIdx.x == 0) {
+                    int prev;
+                    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(prev) : "l"(push->rim_done) : "memory");
+                    if (prev == push->rim_total - 1) {
+                        for (int k = 0; k < push->n_peers; k++)
+                            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(push->signal[k]), "l"(push->seq_signal)
+                                         : "memory");
+                    }
                 }
             }
         }

@@ -477,7 +477,10 @@ class NativeDist:
     def info(self) -> dict:
         i = self._lib.DistInfo()
         self._lib.check(self._L.fs_dist_info(self._h, self._C.byref(i)), "fs_dist_info")
-        return {n: getattr(i, n) for n, _ in i._fields_}
+        out = {n: getattr(i, n) for n, _ in i._fields_}
+        out["phase_ms"] = dict(zip(("advect_drags_div", "sor_with_fused_exchanges", "gradient", "velocity_dye_exchange",
+                                    "dye_advect"), (float(x) for x in i.phase_ms)))
+        return out
 
     def ipc_handle(self) -> bytes:
         buf = self._C.create_string_buffer(64)
@@ -665,6 +668,12 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
     e1.record()
     torch.cuda.synchronize()
     info = sim.info
+    # per-phase times of the last timed step, every rank (max and rank 0)
+    ph = torch.tensor(list(info["phase_ms"].values()), device=dev, dtype=torch.float64)
+    ph_max = ph.clone()
+    dist.all_reduce(ph_max, op=dist.ReduceOp.MAX)
+    phases = {"rank0_ms": dict(zip(info["phase_ms"].keys(), [float(x) for x in ph.tolist()])),
+              "max_over_ranks_ms": dict(zip(info["phase_ms"].keys(), [float(x) for x in ph_max.tolist()]))}
     launches, exchanges = ctx.launch_count - launches0, info["exchanges"] - ex0
     wall_ms = (time.perf_counter() - t0) * 1e3
     pv, pc, pp, pd = sim.device_fields()
@@ -774,6 +783,7 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
         "wall_ms_per_step_max": float(t[1].item()) / args.steps,
         "gpu_launches": int(launches),
         "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": None, "parity": parity,
+        "phases_last_step": phases,
     }
     sim.close()
     return result

@@ -329,6 +329,9 @@ typedef struct fs_dist_info_t {
     int exchanges_per_step;
     unsigned long long exchanges;  /* hand-shakes since creation */
     size_t arena_bytes;
+    float phase_ms[5];      /* the LAST step on this rank, CUDA events: advect+drags+divergence | SOR passes incl.
+                               their fused exchanges | gradient | velocity+dye exchange | dye advect (+ frame);
+                               -1 before the first step.  Querying synchronises with that step. */
 } fs_dist_info_t;
 int fs_dist_create(fs_dist **out, const fs_dist_config *cfg, fs_ctx *ctx);
 int fs_dist_destroy(fs_dist *d);
