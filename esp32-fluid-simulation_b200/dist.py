@@ -91,9 +91,15 @@ class Decomposition:
         self.window = Window(gdim_x, gdim_y, self.gx0 - gl, self.gy0 - gd,
                              (self.gx1 - self.gx0) + gl + gr, (self.gy1 - self.gy0) + gd + gu,
                              gl, gd, gl + (self.gx1 - self.gx0), gd + (self.gy1 - self.gy0))
-        w = self.window
-        assert w.ox >= 0 and w.oy >= 0 and w.ox + w.nx <= gdim_x and w.oy + w.ny <= gdim_y, \
-            "ghost wider than the neighbouring rank's rectangle"
+        # the same verdict on EVERY rank (a rank-local check would let some ranks go on into a collective or a
+        # halo wait while others raise): a strip is cut out of the sender's rectangle, so the ghost width must
+        # not exceed the narrowest rectangle of the decomposition along a cut direction
+        if world > 1 and ghost > 0:
+            ext_x = min(b - a for a, b in (split(gdim_x, self.px, k) for k in range(self.px))) if self.px > 1 else ghost
+            ext_y = min(b - a for a, b in (split(gdim_y, self.py, k) for k in range(self.py))) if self.py > 1 else ghost
+            if ghost > min(ext_x, ext_y):
+                raise ValueError(f"ghost={ghost} is wider than the narrowest rectangle of the {self.px}x{self.py} "
+                                 f"decomposition of {gdim_x}x{gdim_y} ({min(ext_x, ext_y)} nodes)")
 
     def rank_of(self, rx: int, ry: int) -> int | None:
         if 0 <= rx < self.px and 0 <= ry < self.py:
@@ -117,6 +123,8 @@ class Decomposition:
         """Slices (rows, cols) of the window that neighbour (dx,dy) needs: the strip of MY
         rectangle adjacent to it, `width` deep."""
         w = self.window
+        if (dx and width > w.x1 - w.x0) or (dy and width > w.y1 - w.y0):
+            raise ValueError(f"strip of {width} nodes does not fit this rank's {w.x1 - w.x0}x{w.y1 - w.y0} rectangle")
         xs = {-1: slice(w.x0, w.x0 + width), 0: slice(w.x0, w.x1), 1: slice(w.x1 - width, w.x1)}[dx]
         ys = {-1: slice(w.y0, w.y0 + width), 0: slice(w.y0, w.y1), 1: slice(w.y1 - width, w.y1)}[dy]
         return ys, xs
@@ -144,16 +152,17 @@ class DecomposedSim:
     def __init__(self, dec: Decomposition, ops, comm, iters: int, sor_t: int,
                  dt=np.float32(1 / 30.0), dx=np.float32(1.0), omega=np.float32(1.96),
                  static_halo: int | None = None):
-        """static_halo: exchange this many nodes for the advects instead of agreeing on the step's
-        max displacement (saves one all-reduce + host sync per step).  The kernels raise the device
-        status flag (read by `check()`) when a backtrace leaves the WINDOW, so detection is airtight
-        only for static_halo == ghost; with a narrower static halo, backtraces between the two widths
-        would read stale ghosts unnoticed.  None = size every advect halo exactly (always correct, one
-        host sync per step)."""
+        """static_halo: refresh the WHOLE ghost (static_halo == ghost) for the advects instead of agreeing on
+        the step's max displacement (saves one all-reduce + host sync per step).  The kernels raise the
+        device status flag (read by `check()`) when a backtrace leaves the window.  None = size every
+        advect halo exactly (always correct, one host sync per step)."""
         self.dec, self.ops, self.comm = dec, ops, comm
         self.static_halo = static_halo
-        if static_halo is not None and dec.world > 1 and static_halo > dec.ghost:
-            raise ValueError("static_halo exceeds the ghost width")
+        if static_halo is not None and dec.world > 1 and static_halo != dec.ghost:
+            # a backtrace that lands between a narrower static halo and the ghost edge would read stale ghosts
+            # UNNOTICED (the kernels only flag reads outside the window); fs_dist (NativeDist) passes the valid
+            # rectangle to the kernels and may use any width
+            raise ValueError("static_halo must equal the ghost width (or be None: exact halos agreed every step)")
         self.iters, self.sor_t = iters, max(1, sor_t)
         self.dt, self.dx, self.omega = dt, dx, omega
         w = dec.window

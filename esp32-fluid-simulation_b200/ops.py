@@ -40,8 +40,9 @@ def _ptr(a, dtype_name: str, n_elems: int | None = None) -> tuple[int, bool]:
         return 0, False
     if _is_torch(a):
         import torch
-        want = {"float32": torch.float32, "uint32": torch.uint32, "int32": torch.int32,
-                "uint16": torch.uint16, "int16": torch.int16}[dtype_name]
+        # torch.uint32 / torch.uint16 only exist from torch 2.3 on: look them up lazily
+        want = {"float32": torch.float32, "uint32": getattr(torch, "uint32", None), "int32": torch.int32,
+                "uint16": getattr(torch, "uint16", None), "int16": torch.int16}[dtype_name]
         alt = {"uint32": torch.int32, "uint16": torch.int16}.get(dtype_name)
         if a.dtype != want and a.dtype != alt:
             raise TypeError(f"expected {dtype_name} tensor, got {a.dtype}")
