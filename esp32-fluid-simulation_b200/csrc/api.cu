@@ -180,6 +180,16 @@ int fs_ctx_create(fs_ctx **out, int device, void *stream)
     memset(ctx, 0, sizeof(*ctx));
     ctx->device = device;
     ctx->stream = (cudaStream_t)stream;
+    if (stream == FS_STREAM_NEW) {          // a non-blocking stream of the context's own
+        cudaStream_t own;
+        cudaError_t se = cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking);
+        if (se != cudaSuccess) {
+            delete ctx;
+            return (int)se;
+        }
+        ctx->stream = own;
+        ctx->owns_stream = 1;
+    }
     ctx->num_sms = prop.multiProcessorCount;
     ctx->max_smem_optin = prop.sharedMemPerBlockOptin;
     ctx->opt_sor = 1;
@@ -219,6 +229,7 @@ int fs_ctx_destroy(fs_ctx *ctx)
     cudaFree(ctx->rim_dev);
     cudaFree(ctx->halo_done_dev);
     cudaFree(ctx->resid_dev);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
@@ -245,6 +256,7 @@ static int *opt_slot(fs_ctx *ctx, const char *name)
     if (!strcmp(name, "halo_timeout_ms")) return &ctx->opt_halo_timeout_ms;
     if (!strcmp(name, "sor_grid_limit")) return &ctx->opt_sor_grid_limit;
     if (!strcmp(name, "ensemble")) return &ctx->opt_ens;
+    if (!strcmp(name, "num_sms")) return &ctx->num_sms;
     if (!strcmp(name, "advect")) return &ctx->opt_advect;
     if (!strcmp(name, "fuse")) return &ctx->opt_fuse;
     return nullptr;
@@ -257,6 +269,7 @@ int fs_ctx_set_option(fs_ctx *ctx, const char *name, int value)
     int *slot = opt_slot(ctx, name);
     if (!slot) return FS_ERR_INVALID_ARG;
     if (slot == &ctx->opt_sor_t && (value < 1 || value > 8)) return FS_ERR_INVALID_ARG;
+    if (slot == &ctx->num_sms) return FS_ERR_INVALID_ARG;   // read-only
     *slot = value;
     return FS_OK;
 }

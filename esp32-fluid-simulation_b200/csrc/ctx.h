@@ -14,6 +14,7 @@ enum Scratch { S_VTMP = 0, S_CTMP, S_DIV, S_P, S_P2, S_HV, S_HV2, S_HC, S_HC2, S
 struct fs_ctx {
     int device;
     cudaStream_t stream;
+    int owns_stream;            // created by fs_ctx_create(..., FS_STREAM_NEW)
     int num_sms;
     uint64_t launches;
     void *scratch[S_COUNT];

@@ -8,6 +8,11 @@
 //   fluid_harness --gpu-lib <libfluid_b200.so> --cpu-lib <libfluid_ref.so> --cpu-prefix ref_
 //                 [--dim-x 61 --dim-y 81 --steps 20 --iters 10 --drags 4]
 //                 [--gpu-ops advect_v,drags,divergence,poisson,gradient,advect_c | all | none]
+//                 [--decomposed WORLD]
+//
+// --decomposed WORLD adds a third run: the same steps through fs_dist_* (SURVEY.md 8b), WORLD ranks of
+// a block decomposition emulated on device 0 (one context + stream per rank, fs_dist_connect_local),
+// i.e. the C++-sequenced multi-GPU step with its fused halo exchanges, driven from C++.
 //
 // Runs the sequence twice — once all-CPU, once with the selected operators on the GPU —
 // on the same seeded inputs, prints per-operator wall times and FNV-1a hashes of the
@@ -93,6 +98,19 @@ uint64_t fnv(const void *d, size_t n)
 
 struct Drag { uint16_t cx, cy; float vx, vy; };
 
+std::vector<Drag> step_drags(int st, int n_drags, int dim_x, int dim_y)
+{
+    std::vector<Drag> dr(n_drags);
+    for (int k = 0; k < n_drags; k++) {
+        uint64_t h = splitmix(0xD4A6 + (uint64_t)st * 1000 + k);
+        dr[k].cx = (uint16_t)(h % dim_y);
+        dr[k].cy = (uint16_t)((h >> 20) % dim_x);
+        dr[k].vx = (float)((int)((h >> 40) & 0x3ff) - 512);
+        dr[k].vy = (float)((int)((h >> 50) & 0x3ff) - 512);
+    }
+    return dr;
+}
+
 struct State {
     std::vector<float> v, p, d;
     std::vector<uint32_t> c;
@@ -112,14 +130,7 @@ void run(const Ops &o, State &s, int dim_x, int dim_y, int steps, int iters, int
         o.advect_v(v_tmp.data(), s.v.data(), s.v.data(), dim_x, dim_y, dt, 1);             // ino:253
         s.v.swap(v_tmp);                                                                  // ino:255
         double t1 = now();
-        std::vector<Drag> dr(n_drags);
-        for (int k = 0; k < n_drags; k++) {
-            uint64_t h = splitmix(0xD4A6 + (uint64_t)st * 1000 + k);
-            dr[k].cx = (uint16_t)(h % dim_y);
-            dr[k].cy = (uint16_t)((h >> 20) % dim_x);
-            dr[k].vx = (float)((int)((h >> 40) & 0x3ff) - 512);
-            dr[k].vy = (float)((int)((h >> 50) & 0x3ff) - 512);
-        }
+        std::vector<Drag> dr = step_drags(st, n_drags, dim_x, dim_y);
         o.drags(s.v.data(), dr.data(), n_drags, dim_x, dim_y);                            // ino:264-269
         double t2 = now();
         o.divergence(s.d.data(), s.v.data(), dim_x, dim_y, 1.0f);                          // ino:274
@@ -136,12 +147,81 @@ void run(const Ops &o, State &s, int dim_x, int dim_y, int steps, int iters, int
     }
 }
 
+// the same steps through fs_dist_*: `world` ranks of one process on device 0
+int run_decomposed(void *gl, State &s, int dim_x, int dim_y, int steps, int iters, int n_drags, int world)
+{
+    auto ctx_create = (decltype(&fs_ctx_create))must_sym(gl, "fs_ctx_create");
+    auto ctx_destroy = (decltype(&fs_ctx_destroy))must_sym(gl, "fs_ctx_destroy");
+    auto set_opt = (decltype(&fs_ctx_set_option))must_sym(gl, "fs_ctx_set_option");
+    auto get_opt = (decltype(&fs_ctx_get_option))must_sym(gl, "fs_ctx_get_option");
+    auto d_create = (decltype(&fs_dist_create))must_sym(gl, "fs_dist_create");
+    auto d_destroy = (decltype(&fs_dist_destroy))must_sym(gl, "fs_dist_destroy");
+    auto d_window = (decltype(&fs_dist_window))must_sym(gl, "fs_dist_window");
+    auto d_connect = (decltype(&fs_dist_connect_local))must_sym(gl, "fs_dist_connect_local");
+    auto d_upload = (decltype(&fs_dist_upload))must_sym(gl, "fs_dist_upload");
+    auto d_download = (decltype(&fs_dist_download))must_sym(gl, "fs_dist_download");
+    auto d_step = (decltype(&fs_dist_step))must_sym(gl, "fs_dist_step");
+    auto d_check = (decltype(&fs_dist_check))must_sym(gl, "fs_dist_check");
+    G.err = (decltype(G.err))must_sym(gl, "fs_error_string");
+    std::vector<fs_ctx *> ctx(world);
+    std::vector<fs_dist *> rank(world);
+    for (int r = 0; r < world; r++) {
+        gcheck(ctx_create(&ctx[r], 0, FS_STREAM_NEW), "fs_ctx_create");
+        int sms = 0;
+        gcheck(get_opt(ctx[r], "num_sms", &sms), "num_sms");
+        gcheck(set_opt(ctx[r], "sor_grid_limit", sms / world > 0 ? sms / world : 1), "sor_grid_limit");   // all ranks stay resident
+        fs_dist_config cfg = {};
+        cfg.gdim_x = dim_x; cfg.gdim_y = dim_y; cfg.world = world; cfg.rank = r;
+        cfg.ghost = 64; cfg.advect_halo = 24; cfg.iters = iters;
+        cfg.dt = 1 / 30.0f; cfg.dx = 1.0f; cfg.omega = 1.96f;
+        gcheck(d_create(&rank[r], &cfg, ctx[r]), "fs_dist_create");
+    }
+    for (int r = 0; r < world; r++) gcheck(d_connect(rank[r], rank.data()), "fs_dist_connect_local");
+    std::vector<fs_tile> win(world);
+    for (int r = 0; r < world; r++) {
+        gcheck(d_window(rank[r], &win[r]), "fs_dist_window");
+        const fs_tile &w = win[r];
+        std::vector<float> v((size_t)2 * w.nx * w.ny);
+        std::vector<uint32_t> c((size_t)3 * w.nx * w.ny);
+        for (int y = 0; y < w.ny; y++) {
+            std::memcpy(&v[(size_t)2 * y * w.nx], &s.v[2 * ((size_t)(w.oy + y) * dim_x + w.ox)], sizeof(float) * 2 * w.nx);
+            std::memcpy(&c[(size_t)3 * y * w.nx], &s.c[3 * ((size_t)(w.oy + y) * dim_x + w.ox)], sizeof(uint32_t) * 3 * w.nx);
+        }
+        gcheck(d_upload(rank[r], (const fs_vec2f *)v.data(), (const fs_rgb_uq32 *)c.data()), "fs_dist_upload");
+    }
+    for (int st = 0; st < steps; st++) {
+        std::vector<Drag> dr = step_drags(st, n_drags, dim_x, dim_y);
+        for (int r = 0; r < world; r++)      // asynchronous: every rank's step is only enqueued here
+            gcheck(d_step(rank[r], (const fs_drag *)dr.data(), n_drags), "fs_dist_step");
+    }
+    for (int r = 0; r < world; r++) {
+        gcheck(d_check(rank[r]), "fs_dist_check");
+        const fs_tile &w = win[r];
+        const int rw = w.x1 - w.x0, rh = w.y1 - w.y0;
+        std::vector<float> v((size_t)2 * rw * rh), p((size_t)rw * rh), d((size_t)rw * rh);
+        std::vector<uint32_t> c((size_t)3 * rw * rh);
+        gcheck(d_download(rank[r], (fs_vec2f *)v.data(), (fs_rgb_uq32 *)c.data(), p.data(), d.data()), "fs_dist_download");
+        for (int y = 0; y < rh; y++) {
+            const size_t g = (size_t)(w.oy + w.y0 + y) * dim_x + (w.ox + w.x0);
+            std::memcpy(&s.v[2 * g], &v[(size_t)2 * y * rw], sizeof(float) * 2 * rw);
+            std::memcpy(&s.c[3 * g], &c[(size_t)3 * y * rw], sizeof(uint32_t) * 3 * rw);
+            std::memcpy(&s.p[g], &p[(size_t)y * rw], sizeof(float) * rw);
+            std::memcpy(&s.d[g], &d[(size_t)y * rw], sizeof(float) * rw);
+        }
+    }
+    for (int r = 0; r < world; r++) {
+        d_destroy(rank[r]);
+        ctx_destroy(ctx[r]);
+    }
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv)
 {
     std::string gpu_lib, cpu_lib, prefix = "ref_", gpu_ops = "all";
-    int dim_x = 61, dim_y = 81, steps = 20, iters = 10, n_drags = 4;
+    int dim_x = 61, dim_y = 81, steps = 20, iters = 10, n_drags = 4, decomposed = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
@@ -154,9 +234,10 @@ int main(int argc, char **argv)
         else if (a == "--steps") steps = std::atoi(next());
         else if (a == "--iters") iters = std::atoi(next());
         else if (a == "--drags") n_drags = std::atoi(next());
+        else if (a == "--decomposed") decomposed = std::atoi(next());
         else {
             std::printf("usage: %s --cpu-lib LIB [--cpu-prefix ref_|oracle_] [--gpu-lib LIB] [--gpu-ops list|all|none]\n"
-                        "          [--dim-x N --dim-y N --steps N --iters N --drags N]\n", argv[0]);
+                        "          [--dim-x N --dim-y N --steps N --iters N --drags N] [--decomposed WORLD]\n", argv[0]);
             return a == "--help" ? 0 : 2;
         }
     }
@@ -173,9 +254,12 @@ int main(int argc, char **argv)
 
     Ops mixed = cpu;
     bool any_gpu = !gpu_lib.empty() && gpu_ops != "none";
-    if (any_gpu) {
-        void *gl = dlopen(gpu_lib.c_str(), RTLD_NOW | RTLD_LOCAL);
+    void *gl = nullptr;
+    if (any_gpu || (decomposed > 0 && !gpu_lib.empty())) {
+        gl = dlopen(gpu_lib.c_str(), RTLD_NOW | RTLD_LOCAL);
         if (!gl) { std::fprintf(stderr, "dlopen %s: %s\n", gpu_lib.c_str(), dlerror()); return 2; }
+    }
+    if (any_gpu) {
         auto ctx_create = (decltype(&fs_ctx_create))must_sym(gl, "fs_ctx_create");
         G.err = (decltype(G.err))must_sym(gl, "fs_error_string");
         G.advect_vec2f = (decltype(G.advect_vec2f))must_sym(gl, "fsh_advect_vec2f");
@@ -199,6 +283,7 @@ int main(int argc, char **argv)
     for (size_t k = 0; k < 2 * n; k++) a.v[k] = ((float)(splitmix(0xF1D0 + k) >> 40) / 16777216.0f * 2 - 1) * 90.0f;
     for (size_t k = 0; k < 3 * n; k++) a.c[k] = (uint32_t)(splitmix(0xD1E + k) >> 33) * 2u;
     b = a;
+    State dstate = a;
 
     double t_cpu[6] = {0}, t_mix[6] = {0};
     run(cpu, a, dim_x, dim_y, steps, iters, n_drags, t_cpu);
@@ -212,6 +297,13 @@ int main(int argc, char **argv)
     std::printf("  fnv1a64 v/c/p/d  cpu      %016llx %016llx %016llx %016llx\n", (unsigned long long)ha[0], (unsigned long long)ha[1], (unsigned long long)ha[2], (unsigned long long)ha[3]);
     std::printf("  fnv1a64 v/c/p/d  selected %016llx %016llx %016llx %016llx\n", (unsigned long long)hb[0], (unsigned long long)hb[1], (unsigned long long)hb[2], (unsigned long long)hb[3]);
     bool same = !std::memcmp(ha, hb, sizeof(ha));
+    if (decomposed > 0 && gl) {
+        run_decomposed(gl, dstate, dim_x, dim_y, steps, iters, n_drags, decomposed);
+        uint64_t hd[4] = {fnv(dstate.v.data(), 8 * n), fnv(dstate.c.data(), 12 * n), fnv(dstate.p.data(), 4 * n), fnv(dstate.d.data(), 4 * n)};
+        std::printf("  fnv1a64 v/c/p/d  fs_dist  %016llx %016llx %016llx %016llx  (%d ranks)\n", (unsigned long long)hd[0],
+                    (unsigned long long)hd[1], (unsigned long long)hd[2], (unsigned long long)hd[3], decomposed);
+        same = same && !std::memcmp(ha, hd, sizeof(ha));
+    }
     std::printf("%s\n", same ? "MATCH: bit-identical" : "MISMATCH");
     return same ? 0 : 1;
 }

@@ -57,7 +57,9 @@ typedef struct fs_drag {                                      /* struct drag, in
 typedef struct fs_ctx fs_ctx;   /* opaque: device, stream, scratch buffers, TMA descriptors */
 
 /* ---- context -------------------------------------------------------------- */
-/* `stream` is a cudaStream_t (NULL = the legacy default stream). */
+/* `stream` is a cudaStream_t (NULL = the legacy default stream), or FS_STREAM_NEW: the context creates
+ * (and owns) a non-blocking stream — for hosts that do not link the CUDA runtime themselves. */
+#define FS_STREAM_NEW ((void *)(intptr_t)-1)
 int  fs_ctx_create(fs_ctx **out, int device, void *stream);
 int  fs_ctx_destroy(fs_ctx *ctx);
 int  fs_ctx_synchronize(fs_ctx *ctx);
@@ -82,7 +84,8 @@ int  fs_ctx_synchronize(fs_ctx *ctx);
  *              the dye advect (fs_step_frame, fs_advect_rgb_frame, fs_dist with frame = 1);
  *              0 = one kernel per operator; default 5
  *   "sor_grid_limit": cap on the persistent SOR grid, 0 (default) = one CTA per SM; used when several
- *              emulated ranks share one device */
+ *              emulated ranks share one device
+ *   "num_sms": (read-only) SMs of the context's device */
 int  fs_ctx_set_option(fs_ctx *ctx, const char *name, int value);
 int  fs_ctx_get_option(fs_ctx *ctx, const char *name, int *value);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */

@@ -58,3 +58,16 @@ def test_harness_swaps_operators_per_call(built, ops):
         rc, out = run("--cpu-lib", cpu[0], "--cpu-prefix", cpu[1], "--gpu-lib", fb.LIB_PATH, "--gpu-ops", ops,
                       "--dim-x", dims[0], "--dim-y", dims[1], "--steps", "8")
         assert rc == 0 and "MATCH: bit-identical" in out, out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,dims", [(2, ("512", "256")), (4, ("512", "384")), (8, ("1024", "768"))])
+def test_harness_drives_the_decomposed_step_from_cpp(built, world, dims):
+    """fs_dist_* lets the host C++ harness run the multi-GPU step (here: `world` ranks emulated on
+    device 0, each with a context-owned stream) — bit-identical to the CPU library's whole-grid run."""
+    import esp32_fluid_simulation_b200 as fb
+    cpu = (REF_SO, "ref_") if os.path.exists(REF_SO) else (ORACLE_SO, "oracle_")
+    rc, out = run("--cpu-lib", cpu[0], "--cpu-prefix", cpu[1], "--gpu-lib", fb.LIB_PATH, "--gpu-ops", "poisson",
+                  "--dim-x", dims[0], "--dim-y", dims[1], "--steps", "3", "--iters", "20", "--drags", "6",
+                  "--decomposed", str(world))
+    assert rc == 0 and "MATCH: bit-identical" in out and f"({world} ranks)" in out, out
