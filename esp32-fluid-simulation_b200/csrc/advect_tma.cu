@@ -105,6 +105,12 @@ struct TmaAdvectArgs {
     float two_dx_inv;
 };
 
+// (Round 2 built the persistent variant the round-1 review asked for — one CTA per SM slot walking the
+// tiles with a two-stage TMA ring and the next tile's velocities prefetched into registers — and
+// measured it SLOWER: velocity 0.083 vs 0.075 ms, dye 0.151 vs 0.126 ms at 4096^2.  The second stage
+// and the prefetch registers cut the resident CTAs from 3-4 to 2-3 per SM, and this kernel hides its
+// shared-memory and ALU latencies with resident warps, not with a deeper pipeline; one tile per CTA
+// stays.)
 template <class P>
 __global__ void __launch_bounds__(AT_THREADS)
 advect_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
