@@ -546,6 +546,7 @@ def main():
                     "(BASELINE.json configs[3] = 16384x16384, configs[4] = 24576x32768)")
     ap.add_argument("--iters", type=int, default=ITERS, help="SOR iterations per step (N>1 extra configs)")
     ap.add_argument("--upscale", action="store_true", help="N>1: also produce the 4x RGB565 frame every step")
+    ap.add_argument("--no-extra", action="store_true", help="N>1: skip the extra BASELINE configs measured beside the headline")
     ap.add_argument("--no-verify", action="store_true", help="N>1: skip the untimed parity leg (oracle_small, "
                     "one_gpu_equals_n) that runs before the timed region")
     args = ap.parse_args()

@@ -795,7 +795,91 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
         "phases_last_step": phases,
     }
     sim.close()
+    del sim
+    # ---- BASELINE.json configs[3] / [4] beside the headline (only on the driver's default weak-scaling run) ----
+    if not getattr(args, "global_grid", "") and not want_frame and not getattr(args, "no_extra", False):
+        extra = {}
+        try:
+            torch.cuda.empty_cache()
+            extra["config3_16384x16384_k50"] = measure_extra_config(fb, torch, dist, ctx, dev, world, rank, 16384, 16384, 50,
+                                                                    False, ghost, halo, n_drags, steps=10, warmup=3)
+            if world == 8:
+                torch.cuda.empty_cache()
+                extra["config4_24576x32768_k100_frame"] = measure_extra_config(
+                    fb, torch, dist, ctx, dev, world, rank, 24576, 32768, 100, True, ghost, halo, n_drags, steps=5, warmup=2)
+        except Exception as e:  # noqa: BLE001 — an extra must never take the headline down (every rank reaches the barrier below)
+            extra["error"] = f"{type(e).__name__}: {e}"
+        result["extra"] = extra
     return result
+
+
+def measure_extra_config(fb, torch, dist, ctx, dev, world, rank, gx, gy, iters, frame, ghost, halo, n_drags, steps, warmup):
+    """One more decomposed configuration, timed like the headline (CUDA events, max over ranks), with its
+    same-size single-GPU denominator: this rank's rectangle stepped as a whole grid on this GPU alone."""
+    from . import synth
+    sim = NativeDist(ctx, gx, gy, world, rank, iters, ghost=ghost, advect_halo=halo, dt=synth.DT, dx=synth.DX,
+                     omega=synth.OMEGA, frame=frame)
+    handles = [None] * world
+    dist.all_gather_object(handles, sim.ipc_handle())
+    sim.connect(handles)
+    w = sim.window
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    v = (torch.rand(w.ny, w.nx, 2, device=dev, generator=g) - 0.5) * 120.0      # +-60 nodes/s like synth.velocity
+    c = torch.randint(0, 2 ** 31 - 1, (w.ny, w.nx, 3), device=dev, dtype=torch.int32, generator=g)
+    sim.upload(v, c)
+    del v, c
+    drags = [synth.drags(gx, gy, s, n=n_drags) for s in range(warmup + steps)]
+    for s in range(warmup):
+        sim.step(drags[s])
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(warmup, warmup + steps):
+        sim.step(drags[s])
+    e1.record()
+    torch.cuda.synchronize()
+    sim.check()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    info = sim.info
+    own_w, own_h = w.x1 - w.x0, w.y1 - w.y0
+    sim.close()
+    del sim
+    torch.cuda.empty_cache()
+    # the denominator: the same rectangle as a whole grid on one GPU (fs_step_pingpong / fs_step_frame)
+    g = torch.Generator(device=dev).manual_seed(7)
+    v1 = (torch.rand(own_h, own_w, 2, device=dev, generator=g) - 0.5) * 120.0
+    c1 = torch.randint(0, 2 ** 31 - 1, (own_h, own_w, 3), device=dev, dtype=torch.int32, generator=g)
+    c2 = torch.empty_like(c1)
+    fr = torch.empty((own_w - 1) * 4, (own_h - 1) * 4, dtype=torch.int16, device=dev) if frame else None
+    dyes = [c1, c2]
+
+    def one(k):
+        if frame:
+            ctx.step_frame(v1, dyes[k & 1], dyes[(k & 1) ^ 1], fr, drags[k % len(drags)], own_w, own_h, synth.DT, synth.DX, iters,
+                           synth.OMEGA)
+        else:
+            ctx.step_pingpong(v1, dyes[k & 1], dyes[(k & 1) ^ 1], drags[k % len(drags)], own_w, own_h, synth.DT, synth.DX,
+                              iters, synth.OMEGA)
+
+    for k in range(warmup):
+        one(k)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for k in range(warmup, warmup + steps):
+        one(k)
+    s1.record()
+    torch.cuda.synchronize()
+    t1 = torch.tensor([s0.elapsed_time(s1) / steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+    ms, ms1 = float(t.item()), float(t1.item())
+    del v1, c1, c2, fr
+    torch.cuda.empty_cache()
+    return {"grid": [gx, gy], "sor_iters": iters, "frame": bool(frame), "n_gpus": world, "nodes_per_gpu": [own_w, own_h],
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "mcell_steps_per_s": gx * gy / (ms * 1e-3) / 1e6,
+            "one_gpu_same_rectangle_ms": ms1, "efficiency_vs_one_gpu_same_rectangle": ms1 / ms,
+            "exchanges_per_step": info["exchanges_per_step"], "data": "synthetic (device-generated uniform fields)"}
 
 
 def bench_decomposed_python(args, tile_edge: int, iters: int, n_drags: int, mode: str) -> dict:
