@@ -151,12 +151,23 @@ def run_reference_arm(args):
     rate, sec, kind = cpu_step_rate(dim_x, dim_y, steps, warmup)
     sample = (f"{steps} timed + {warmup} warm-up full loop() bodies on the whole {dim_x}x{dim_y} grid, "
               f"K={ITERS}, {N_DRAGS} drags; single thread pinned to core {core} (the reference is single-threaded)")
+    workload = f"single {GRID}x{GRID} grid, {ITERS} SOR iterations, velocity + dye advection"
+    same = True
+    if args.gpus > 1:
+        # the B200 arm's N>1 workload is one grid of 4096^2 nodes PER GPU; the single-threaded reference is timed
+        # on one rank's share of it per step (the whole grid would take N x 4 s per step); the metric is a rate
+        from esp32_fluid_simulation_b200.dist import process_grid
+        px, py = process_grid(args.gpus)
+        workload = (f"{GRID * px}x{GRID * py} grid ({GRID}x{GRID} nodes per GPU on the B200 arm), {ITERS} SOR iterations, "
+                    "velocity + dye advection")
+        sample += f"; bounded sample: one {GRID}x{GRID} rectangle (one rank's share of the {GRID * px}x{GRID * py} grid) per step"
+        same = False
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+uq32", "data": "synthetic",
-        "config": {"workload": f"single {GRID}x{GRID} grid, {ITERS} SOR iterations, velocity + dye advection",
-                   "grid": [dim_x, dim_y], "sor_iters": ITERS, "drags_per_step": N_DRAGS, "same_config": True,
+        "config": {"workload": workload,
+                   "grid": [dim_x, dim_y], "sor_iters": ITERS, "drags_per_step": N_DRAGS, "same_config": same,
                    "sample": sample},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
