@@ -521,7 +521,19 @@ def bench_single(args, fb, synth, torch):
     state_bytes = nodes * (8 + 12)
     e2e = {"value": nodes / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": state_bytes + 12 * N_DRAGS,
            "d2h_bytes_per_step": state_bytes, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-           "api": "fsh_step (host pointers in, host pointers out; pinned buffers)"}
+           "api": "fsh_step (host pointers in, host pointers out; pinned buffers)",
+           "dye_bands": ctx.get_option("e2e_bands"), "dye_redos": ctx.get_option("e2e_redos")}
+    # the same call with the dye travelling in fewer / more row bands (PCIe-bound either way: 20 B/node each direction)
+    band_ms = {}
+    for bands in (1, 4, 16):
+        ctx.set_option("e2e_bands", bands)
+        ctx.step(hv_np, hc_np, drags[0], n, ny, synth.DT, synth.DX, ITERS, synth.OMEGA)
+        t0 = time.perf_counter()
+        for s in range(3):
+            ctx.step(hv_np, hc_np, drags[s % len(drags)], n, ny, synth.DT, synth.DX, ITERS, synth.OMEGA)
+        band_ms[str(bands)] = round((time.perf_counter() - t0) / 3 * 1e3, 3)
+    ctx.set_option("e2e_bands", e2e["dye_bands"])
+    extra["e2e_ms_by_dye_bands"] = band_ms
 
     # --- cpu baseline beside it (bounded: 2 full-size steps, ~12 s) ---
     cpu = None

@@ -79,12 +79,56 @@ struct TileFetch {
 
 // The general `sample` (walls, corners, backtraces that leave the staged tile) is kept out of line:
 // the unrolled per-row loop then only carries the short interior path, and the kernel stays inside
-// the instruction cache (ncu: `no_instruction` was the top stall with it inlined 8 times).
+// the instruction cache (ncu: `no_instruction` was the top stall with it inlined 8 times).  The result
+// comes back by value, in registers: an out-parameter put every node's result through local memory.
+template <class P>
+struct Raw {
+    typename P::raw_t v[P::NC];
+};
 template <class P, class F>
-__device__ __noinline__ void sample_slow(typename P::raw_t (&out)[P::NC], const F &fetch, float si, float sj,
-                                         int GX, int GY, bool no_slip)
+__device__ __noinline__ Raw<P> sample_slow(const F &fetch, float si, float sj, int GX, int GY, bool no_slip)
 {
-    sample<P>(out, fetch, si, sj, GX, GY, no_slip);
+    Raw<P> r;
+    sample<P>(r.v, fetch, si, sj, GX, GY, no_slip);
+    return r;
+}
+
+// Where the straight-line interior path applies (CTA-uniform): the bilinear cell (tx..tx+1, ty..ty+1)
+// must be staged AND inside the valid part of this rank's window (outside the window the hardware
+// zero-filled the tile).  Two unsigned compares on the floored source replace advect.h:26-29's four
+// float compares: the valid rectangle lies inside the domain, so floor(si) in [vx0, vx1-1) already
+// gives 0 <= si < GX-1 (advect.h:38, "!x_oob && !y_oob"); a source beyond +-2^31 saturates the
+// conversion and fails the range test.
+struct FastWindow {
+    int cx, cy;              // global node whose cell is the first one on the fast path
+    unsigned x_span, y_span; // cells on the fast path each way
+    int toff;                // word offset of that node in the staged tile
+};
+template <int NC>
+__device__ __forceinline__ FastWindow fast_window(const Geo &g, int bx0, int by0, int W, int H)
+{
+    const int tx_lo = max(0, g.vx0 - bx0), tx_hi = min(W - 1, g.vx1 - 1 - bx0);   // tx in [tx_lo, tx_hi)
+    const int ty_lo = max(0, g.vy0 - by0), ty_hi = min(H - 1, g.vy1 - 1 - by0);
+    FastWindow f;
+    f.cx = g.ox + bx0 + tx_lo;
+    f.cy = g.oy + by0 + ty_lo;
+    f.x_span = (unsigned)max(0, tx_hi - tx_lo);
+    f.y_span = (unsigned)max(0, ty_hi - ty_lo);
+    f.toff = (ty_lo * W + tx_lo) * NC;
+    return f;
+}
+// true: (tx, ty) = the cell relative to FastWindow's first node, (di, dj) = advect.h:34-35's fractions
+// (float(int(floor(s))) == floorf(s) exactly for every s that passes the range test)
+__device__ __forceinline__ bool fast_cell(const FastWindow &f, float si, float sj, int &tx, int &ty, float &di,
+                                          float &dj)
+{
+    const int gi = __float2int_rd(si), gj = __float2int_rd(sj);
+    tx = gi - f.cx;
+    ty = gj - f.cy;
+    if ((unsigned)tx >= f.x_span || (unsigned)ty >= f.y_span) return false;
+    di = __fsub_rn(si, (float)gi);
+    dj = __fsub_rn(sj, (float)gj);
+    return true;
 }
 
 struct TmaAdvectArgs {
@@ -111,13 +155,14 @@ struct TmaAdvectArgs {
 // and the prefetch registers cut the resident CTAs from 3-4 to 2-3 per SM, and this kernel hides its
 // shared-memory and ALU latencies with resident warps, not with a deeper pipeline; one tile per CTA
 // stays.)
-template <class P>
+template <class P, bool STORE_TMA>
 __global__ void __launch_bounds__(AT_THREADS)
 advect_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                   const TmaAdvectArgs a)
 {
     using raw_t = typename P::raw_t;
     using TS = TileShape<P>;
+    static_assert(!STORE_TMA || P::NC == 3, "only the dye leaves through a bulk-tensor store");
     extern __shared__ __align__(128) unsigned char smem[];
     raw_t *tile = reinterpret_cast<raw_t *>(smem);
     raw_t *otile = reinterpret_cast<raw_t *>(smem + ((TS::IN_BYTES + 127) & ~127));
@@ -157,19 +202,16 @@ advect_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
 
     TileFetch<P> fetch{tile, reinterpret_cast<const raw_t *>(a.p), bx0, by0, g.ox, g.oy, g.nx,
                        g.vx0, g.vy0, g.vx1 - g.vx0, g.vy1 - g.vy0, a.status};
-    // Fast path bounds (CTA-uniform): the bilinear cell (tx..tx+1, ty..ty+1) must be staged AND inside
-    // the valid part of this rank's window (outside the window the hardware zero-filled the tile).
-    const int tx_lo = max(0, g.vx0 - bx0), tx_hi = min(TS::W - 1, g.vx1 - 1 - bx0);   // tx in [tx_lo, tx_hi)
-    const int ty_lo = max(0, g.vy0 - by0), ty_hi = min(TS::H - 1, g.vy1 - 1 - by0);
-    const float x_max = (float)(g.GX - 1), y_max = (float)(g.GY - 1);
+    const FastWindow fw = fast_window<P::NC>(g, bx0, by0, TS::W, TS::H);
+    const raw_t *ftile = tile + fw.toff;
 #pragma unroll
     for (int it = 0; it < ITERS; it++) {
         const int ry = cy + it * ROWS_PER_IT;
         const int lx = tx0 + cx, ly = ty0 + ry;
         const bool live = lx < g.x1 && ly < g.y1;
-        raw_t out[P::NC];
+        Raw<P> out;
 #pragma unroll
-        for (int ch = 0; ch < P::NC; ch++) out[ch] = 0;
+        for (int ch = 0; ch < P::NC; ch++) out.v[ch] = 0;
         if (live) {
             float2 vv;
             if (a.vel_is_p) {
@@ -180,57 +222,52 @@ advect_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             } else {
                 vv = vel[it];
             }
-            float si, sj;
+            float si, sj, di, dj;
+            int tx, ty;
             backtrace(si, sj, g.ox + lx, g.oy + ly, vv, a.dt);
             // interior (advect.h:38: !x_oob && !y_oob) with all four corners staged: straight-line path
-            const float fi = floorf(si), fj = floorf(sj);
-            const int tx = (int)fi - g.ox - bx0, ty = (int)fj - g.oy - by0;
-            const bool interior = si >= 0.0f && si < x_max && sj >= 0.0f && sj < y_max;
-            if (interior && tx >= tx_lo && tx < tx_hi && ty >= ty_lo && ty < ty_hi) {
-                const float di = __fsub_rn(si, fi), dj = __fsub_rn(sj, fj);
+            if (fast_cell(fw, si, sj, tx, ty, di, dj)) {
                 const float wi = __fsub_rn(1.0f, di), wj = __fsub_rn(1.0f, dj);
-                const raw_t *q = tile + ty * TS::ROW_WORDS + tx * P::NC;
+                const raw_t *q = ftile + ty * TS::ROW_WORDS + tx * P::NC;
                 if constexpr (P::NC == 2) {
                     const float2 p11 = *reinterpret_cast<const float2 *>(q);
                     const float2 p21 = *reinterpret_cast<const float2 *>(q + 2);
                     const float2 p12 = *reinterpret_cast<const float2 *>(q + TS::ROW_WORDS);
                     const float2 p22 = *reinterpret_cast<const float2 *>(q + TS::ROW_WORDS + 2);
-                    out[0] = mixf(wi, di, mixf(wj, dj, p11.x, p12.x), mixf(wj, dj, p21.x, p22.x));
-                    out[1] = mixf(wi, di, mixf(wj, dj, p11.y, p12.y), mixf(wj, dj, p21.y, p22.y));
+                    out.v[0] = mixf(wi, di, mixf(wj, dj, p11.x, p12.x), mixf(wj, dj, p21.x, p22.x));
+                    out.v[1] = mixf(wi, di, mixf(wj, dj, p11.y, p12.y), mixf(wj, dj, p21.y, p22.y));
                 } else {
 #pragma unroll
                     for (int ch = 0; ch < 3; ch++) {
                         const float a11 = uq32_to_float(q[ch]), a21 = uq32_to_float(q[3 + ch]);
                         const float a12 = uq32_to_float(q[TS::ROW_WORDS + ch]);
                         const float a22 = uq32_to_float(q[TS::ROW_WORDS + 3 + ch]);
-                        out[ch] = uq32_from_float(mixf(wi, di, mixf(wj, dj, a11, a12), mixf(wj, dj, a21, a22)));
+                        out.v[ch] = uq32_from_float(mixf(wi, di, mixf(wj, dj, a11, a12), mixf(wj, dj, a21, a22)));
                     }
                 }
             } else {
-                sample_slow<P>(out, fetch, si, sj, g.GX, g.GY, a.no_slip != 0);
+                out = sample_slow<P>(fetch, si, sj, g.GX, g.GY, a.no_slip != 0);
             }
         }
         if constexpr (P::NC == 2) {
-            if (live) reinterpret_cast<float2 *>(a.next_p)[(size_t)ly * g.nx + lx] = make_float2(out[0], out[1]);
+            if (live) reinterpret_cast<float2 *>(a.next_p)[(size_t)ly * g.nx + lx] = make_float2(out.v[0], out.v[1]);
+        } else if constexpr (STORE_TMA) {
+            raw_t *q = otile + (ry * AT_TX + cx) * 3;
+            q[0] = out.v[0]; q[1] = out.v[1]; q[2] = out.v[2];
         } else {
-            if (a.store_tma) {
-                raw_t *q = otile + (ry * AT_TX + cx) * 3;
-                q[0] = out[0]; q[1] = out[1]; q[2] = out[2];
-            } else if (live) {
+            if (live) {
                 raw_t *q = reinterpret_cast<raw_t *>(a.next_p) + ((size_t)ly * g.nx + lx) * 3;
-                q[0] = out[0]; q[1] = out[1]; q[2] = out[2];
+                q[0] = out.v[0]; q[1] = out.v[1]; q[2] = out.v[2];
             }
         }
     }
-    if constexpr (P::NC == 3) {
-        if (a.store_tma) {
-            // out_map describes the compute rectangle only, so the hardware clips partial tiles
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                tma_store_2d(&out_map, blockIdx.x * AT_TX * 3, blockIdx.y * AT_TY, otile);
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            }
+    if constexpr (STORE_TMA) {
+        // out_map describes the compute rectangle only, so the hardware clips partial tiles
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tma_store_2d(&out_map, blockIdx.x * AT_TX * 3, blockIdx.y * AT_TY, otile);
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
     }
 }
@@ -283,41 +320,47 @@ advect_div_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_c
     }
     TileFetch<P, AD_W, AD_H> fetch{tile, reinterpret_cast<const float *>(a.v_in), bx0, by0, g.ox, g.oy, g.nx,
                                    g.vx0, g.vy0, g.vx1 - g.vx0, g.vy1 - g.vy0, a.status};
-    const int tx_lo = max(0, g.vx0 - bx0), tx_hi = min(AD_W - 1, g.vx1 - 1 - bx0);
-    const int ty_lo = max(0, g.vy0 - by0), ty_hi = min(AD_H - 1, g.vy1 - 1 - by0);
-    const float x_max = (float)(g.GX - 1), y_max = (float)(g.GY - 1);
+    const FastWindow fw = fast_window<2>(g, bx0, by0, AD_W, AD_H);
+    const float *ftile = tile + fw.toff;
+    // only the compute rectangle and its one-node ring are advected (partial tiles stick out of it; on a
+    // decomposed grid nodes further out would backtrace into ghosts that were never refreshed):
+    // in (ax, ay) = position in the advected tile + ring
+    const int ax_lo = max(g.x0 - 1, 0) - (tx0 - 1), ay_lo = max(g.y0 - 1, 0) - (ty0 - 1);
+    const unsigned ax_span = (unsigned)max(0, min(g.x1 + 1, g.nx) - (tx0 - 1) - ax_lo);
+    const unsigned ay_span = (unsigned)max(0, min(g.y1 + 1, g.ny) - (ty0 - 1) - ay_lo);
     mbar_wait(&bar, 0);
 
     // ---- advect tile + ring into shared memory ----
+    int ay = threadIdx.x / AD_AW, ax = threadIdx.x - ay * AD_AW;
 #pragma unroll 1
     for (int k = threadIdx.x; k < AD_AW * AD_AH; k += AT_THREADS) {
-        const int ay = k / AD_AW, ax = k - ay * AD_AW;
-        const int lx = tx0 - 1 + ax, ly = ty0 - 1 + ay;
-        float out[2] = {0.f, 0.f};
-        // only the compute rectangle and its one-node ring (partial tiles stick out of it; on a
-        // decomposed grid nodes further out would backtrace into ghosts that were never refreshed)
-        if (lx >= max(g.x0 - 1, 0) && lx < min(g.x1 + 1, g.nx) && ly >= max(g.y0 - 1, 0) && ly < min(g.y1 + 1, g.ny)) {
+        float2 out = make_float2(0.f, 0.f);
+        if ((unsigned)(ax - ax_lo) < ax_span && (unsigned)(ay - ay_lo) < ay_span) {
             const float2 vv = *reinterpret_cast<const float2 *>(tile + (ay + AT_HALO) * ROW_WORDS + (ax + AD_LEFT - 1) * 2);
-            float si, sj;
-            backtrace(si, sj, g.ox + lx, g.oy + ly, vv, a.dt);
-            const float fi = floorf(si), fj = floorf(sj);
-            const int tx = (int)fi - g.ox - bx0, ty = (int)fj - g.oy - by0;
-            const bool interior = si >= 0.0f && si < x_max && sj >= 0.0f && sj < y_max;
-            if (interior && tx >= tx_lo && tx < tx_hi && ty >= ty_lo && ty < ty_hi) {
-                const float di = __fsub_rn(si, fi), dj = __fsub_rn(sj, fj);
+            float si, sj, di, dj;
+            int tx, ty;
+            backtrace(si, sj, g.ox + tx0 - 1 + ax, g.oy + ty0 - 1 + ay, vv, a.dt);
+            if (fast_cell(fw, si, sj, tx, ty, di, dj)) {
                 const float wi = __fsub_rn(1.0f, di), wj = __fsub_rn(1.0f, dj);
-                const float *q = tile + ty * ROW_WORDS + tx * 2;
+                const float *q = ftile + ty * ROW_WORDS + tx * 2;
                 const float2 p11 = *reinterpret_cast<const float2 *>(q);
                 const float2 p21 = *reinterpret_cast<const float2 *>(q + 2);
                 const float2 p12 = *reinterpret_cast<const float2 *>(q + ROW_WORDS);
                 const float2 p22 = *reinterpret_cast<const float2 *>(q + ROW_WORDS + 2);
-                out[0] = mixf(wi, di, mixf(wj, dj, p11.x, p12.x), mixf(wj, dj, p21.x, p22.x));
-                out[1] = mixf(wi, di, mixf(wj, dj, p11.y, p12.y), mixf(wj, dj, p21.y, p22.y));
+                out.x = mixf(wi, di, mixf(wj, dj, p11.x, p12.x), mixf(wj, dj, p21.x, p22.x));
+                out.y = mixf(wi, di, mixf(wj, dj, p11.y, p12.y), mixf(wj, dj, p21.y, p22.y));
             } else {
-                sample_slow<P>(out, fetch, si, sj, g.GX, g.GY, true);
+                const Raw<P> r = sample_slow<P>(fetch, si, sj, g.GX, g.GY, true);
+                out = make_float2(r.v[0], r.v[1]);
             }
         }
-        adv[k] = make_float2(out[0], out[1]);
+        adv[k] = out;
+        ax += AT_THREADS % AD_AW;                       // k += AT_THREADS without the division
+        ay += AT_THREADS / AD_AW;
+        if (ax >= AD_AW) {
+            ax -= AD_AW;
+            ay++;
+        }
     }
     __syncthreads();
 
@@ -422,43 +465,40 @@ advect_rgb_frame_kernel(const __grid_constant__ CUtensorMap in_map, const FrameA
     mbar_wait(&bar, 0);
 
     TileFetch<P, FR_W, FR_H> fetch{tile, a.c, bx0, by0, g.ox, g.oy, g.nx, g.vx0, g.vy0, g.vx1 - g.vx0, g.vy1 - g.vy0, a.status};
-    const int tx_lo = max(0, g.vx0 - bx0), tx_hi = min(FR_W - 1, g.vx1 - 1 - bx0);
-    const int ty_lo = max(0, g.vy0 - by0), ty_hi = min(FR_H - 1, g.vy1 - 1 - by0);
-    const float x_max = (float)(g.GX - 1), y_max = (float)(g.GY - 1);
+    const FastWindow fw = fast_window<3>(g, bx0, by0, FR_W, FR_H);
+    const uint32_t *ftile = tile + fw.toff;
 #pragma unroll
     for (int it = 0; it < FR_ITERS; it++) {
         const int k = threadIdx.x + it * AT_THREADS;
         if (k >= FR_NX * FR_NY) break;
         const int ny = k / FR_NX, nx = k - ny * FR_NX;
         const int lx = tx0 + nx, ly = ty0 + ny;
-        uint32_t out[3] = {0u, 0u, 0u};
+        Raw<P> out;
+        out.v[0] = out.v[1] = out.v[2] = 0u;
         if (lx < lim_x && ly < lim_y) {
-            float si, sj;
+            float si, sj, di, dj;
+            int tx, ty;
             backtrace(si, sj, g.ox + lx, g.oy + ly, vel[it], a.dt);
-            const float fi = floorf(si), fj = floorf(sj);
-            const int tx = (int)fi - g.ox - bx0, ty = (int)fj - g.oy - by0;
-            const bool interior = si >= 0.0f && si < x_max && sj >= 0.0f && sj < y_max;
-            if (interior && tx >= tx_lo && tx < tx_hi && ty >= ty_lo && ty < ty_hi) {
-                const float di = __fsub_rn(si, fi), dj = __fsub_rn(sj, fj);
+            if (fast_cell(fw, si, sj, tx, ty, di, dj)) {
                 const float wi = __fsub_rn(1.0f, di), wj = __fsub_rn(1.0f, dj);
-                const uint32_t *q = tile + ty * FR_ROW_WORDS + tx * 3;
+                const uint32_t *q = ftile + ty * FR_ROW_WORDS + tx * 3;
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) {
                     const float a11 = uq32_to_float(q[ch]), a21 = uq32_to_float(q[3 + ch]);
                     const float a12 = uq32_to_float(q[FR_ROW_WORDS + ch]);
                     const float a22 = uq32_to_float(q[FR_ROW_WORDS + 3 + ch]);
-                    out[ch] = uq32_from_float(mixf(wi, di, mixf(wj, dj, a11, a12), mixf(wj, dj, a21, a22)));
+                    out.v[ch] = uq32_from_float(mixf(wi, di, mixf(wj, dj, a11, a12), mixf(wj, dj, a21, a22)));
                 }
             } else {
-                sample_slow<P>(out, fetch, si, sj, g.GX, g.GY, a.no_slip != 0);
+                out = sample_slow<P>(fetch, si, sj, g.GX, g.GY, a.no_slip != 0);
             }
             if (nx < AT_TX && ny < AT_TY && lx < g.x1 && ly < g.y1) {      // the tile itself: the advected dye
                 uint32_t *q = a.next_c + ((size_t)ly * g.nx + lx) * 3;
-                q[0] = out[0]; q[1] = out[1]; q[2] = out[2];
+                q[0] = out.v[0]; q[1] = out.v[1]; q[2] = out.v[2];
             }
         }
         uint32_t *e = ext + ny * FR_EXT_PITCH + nx * 3;
-        e[0] = out[0]; e[1] = out[1]; e[2] = out[2];
+        e[0] = out.v[0]; e[1] = out.v[1]; e[2] = out.v[2];
     }
     __syncthreads();
 
@@ -522,11 +562,13 @@ static int launch_tma(const Launch &L, void *next_p, const void *p, const float2
             a.store_tma = 1;
     }
     const size_t smem = ((TS::IN_BYTES + 127) & ~127) + TS::OUT_BYTES;
-    cudaError_t e = cudaFuncSetAttribute(advect_tma_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    auto kern = advect_tma_kernel<P, false>;
+    if constexpr (P::NC == 3)
+        if (a.store_tma) kern = advect_tma_kernel<P, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((w + AT_TX - 1) / AT_TX, (h + AT_TY - 1) / AT_TY);
-    advect_tma_kernel<P><<<grid, AT_THREADS, smem, L.stream>>>(in_map, out_map, a);
+    kern<<<grid, AT_THREADS, smem, L.stream>>>(in_map, out_map, a);
     ++*L.launches;
     return (int)cudaGetLastError();
 }
@@ -640,8 +682,9 @@ int launch_advect_rgb_tma_grad(const Launch &L, uint32_t *next_c, const uint32_t
 
 int preload_advect_tma_kernels()
 {
-    FS_PRELOAD(advect_tma_kernel<Vec2Payload>);
-    FS_PRELOAD(advect_tma_kernel<RgbPayload>);
+    FS_PRELOAD((advect_tma_kernel<Vec2Payload, false>));
+    FS_PRELOAD((advect_tma_kernel<RgbPayload, false>));
+    FS_PRELOAD((advect_tma_kernel<RgbPayload, true>));
     FS_PRELOAD(advect_div_tma_kernel);
     FS_PRELOAD(advect_rgb_frame_kernel);
     return 0;

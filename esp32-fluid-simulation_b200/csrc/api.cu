@@ -141,6 +141,11 @@ int ensure_copy_streams(fs_ctx *ctx)
     FS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
     FS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_c_in, cudaEventDisableTiming));
     FS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_v_done, cudaEventDisableTiming));
+    for (int b = 0; b < E2E_MAX_BANDS; b++) {
+        FS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_band_in[b], cudaEventDisableTiming));
+        FS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_band_done[b], cudaEventDisableTiming));
+    }
+    FS_CUDA_TRY(cudaMalloc(&ctx->band_flag_dev, sizeof(int)));
     return FS_OK;
 }
 
@@ -200,6 +205,7 @@ int fs_ctx_create(fs_ctx **out, int device, void *stream)
     ctx->opt_ens = 0;
     ctx->opt_advect = 1;
     ctx->opt_fuse = 5;
+    ctx->opt_e2e_bands = 8;
     cudaError_t e = cudaMalloc(&ctx->status_dev, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->maxdisp_dev, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->work_dev, WORK_SLOTS * sizeof(int));
@@ -235,6 +241,11 @@ int fs_ctx_destroy(fs_ctx *ctx)
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_c_in) cudaEventDestroy(ctx->ev_c_in);
     if (ctx->ev_v_done) cudaEventDestroy(ctx->ev_v_done);
+    for (int b = 0; b < E2E_MAX_BANDS; b++) {
+        if (ctx->ev_band_in[b]) cudaEventDestroy(ctx->ev_band_in[b]);
+        if (ctx->ev_band_done[b]) cudaEventDestroy(ctx->ev_band_done[b]);
+    }
+    if (ctx->band_flag_dev) cudaFree(ctx->band_flag_dev);
     delete ctx;
     return FS_OK;
 }
@@ -259,6 +270,8 @@ static int *opt_slot(fs_ctx *ctx, const char *name)
     if (!strcmp(name, "num_sms")) return &ctx->num_sms;
     if (!strcmp(name, "advect")) return &ctx->opt_advect;
     if (!strcmp(name, "fuse")) return &ctx->opt_fuse;
+    if (!strcmp(name, "e2e_bands")) return &ctx->opt_e2e_bands;
+    if (!strcmp(name, "e2e_redos")) return &ctx->stat_e2e_redos;
     return nullptr;
 }
 
@@ -269,7 +282,8 @@ int fs_ctx_set_option(fs_ctx *ctx, const char *name, int value)
     int *slot = opt_slot(ctx, name);
     if (!slot) return FS_ERR_INVALID_ARG;
     if (slot == &ctx->opt_sor_t && (value < 1 || value > 8)) return FS_ERR_INVALID_ARG;
-    if (slot == &ctx->num_sms) return FS_ERR_INVALID_ARG;   // read-only
+    if (slot == &ctx->num_sms || slot == &ctx->stat_e2e_redos) return FS_ERR_INVALID_ARG;   // read-only
+    if (slot == &ctx->opt_e2e_bands && (value < 1 || value > E2E_MAX_BANDS)) return FS_ERR_INVALID_ARG;
     *slot = value;
     return FS_OK;
 }
@@ -692,16 +706,32 @@ int fsh_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags, int n_drags, int
     if ((e = ensure(ctx, S_P, n * sizeof(float), &d_p))) return e;
     if ((e = ensure(ctx, S_DIV, n * sizeof(float), &d_div))) return e;
     if ((e = ensure_copy_streams(ctx))) return e;
-    // The step is PCIe-bound (20 B/node each way).  Only the velocity is needed up front: the dye
-    // upload rides a side stream under the velocity phase, and the projected velocity goes home on a
-    // second side stream (the other PCIe direction) while the dye is still arriving.
+    // The step is PCIe-bound (20 B/node each way), so the schedule is built around the two copy engines.
+    // Up: velocity first (the only thing the projection needs), then the dye in row bands on a side
+    // stream under the velocity phase.  Down: the projected velocity leaves on a second side stream as
+    // soon as it exists, and dye band b follows as soon as it is advected — which needs the projected
+    // velocity and dye bands 0..b+1 only, so the last bands are still arriving while the first ones go
+    // home.  A backtrace longer than a band (>= 128 rows) would read dye that has not arrived: the
+    // advect's valid-rectangle check raises a flag instead of using it, and the dye is then advected
+    // again in one piece once everything is here.
     const Geo g = geo_full(dim_x, dim_y);
+    int bands = ctx->opt_e2e_bands;
+    if (bands > dim_y / 128) bands = dim_y / 128;
+    if (bands < 1 || !advect_rgb_tma_legal((const uint32_t *)d_c, g)) bands = 1;
+    int row0[E2E_MAX_BANDS + 1];
+    for (int b = 0; b <= bands; b++) row0[b] = b == bands ? dim_y : (int)((long long)dim_y * b / bands) / 32 * 32;
+    const size_t row_c = (size_t)dim_x * sizeof(fs_rgb_uq32);
     FS_CUDA_TRY(cudaEventRecord(ctx->ev_start, ctx->stream));          // earlier work on the scratch buffers
     FS_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_start, 0));
     FS_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_start, 0));
     H2D(d_v, v, n * sizeof(fs_vec2f));
-    FS_CUDA_TRY(cudaMemcpyAsync(d_c, c, n * sizeof(fs_rgb_uq32), cudaMemcpyHostToDevice, ctx->copy_in));
-    FS_CUDA_TRY(cudaEventRecord(ctx->ev_c_in, ctx->copy_in));
+    FS_CUDA_TRY(cudaEventRecord(ctx->ev_c_in, ctx->stream));           // the velocity owns the link first
+    FS_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_c_in, 0));
+    for (int b = 0; b < bands; b++) {
+        FS_CUDA_TRY(cudaMemcpyAsync((char *)d_c + row0[b] * row_c, (const char *)c + row0[b] * row_c,
+                                    (row0[b + 1] - row0[b]) * row_c, cudaMemcpyHostToDevice, ctx->copy_in));
+        FS_CUDA_TRY(cudaEventRecord(ctx->ev_band_in[b], ctx->copy_in));
+    }
     if ((e = core_step_velocity(ctx, (fs_vec2f *)d_v, (fs_vec2f *)d_vtmp, drags, n_drags, g, dt, dx, iters,
                                 omega, (float *)d_p, (float *)d_div)))
         return e;
@@ -712,12 +742,42 @@ int fsh_step(fs_vec2f *v, fs_rgb_uq32 *c, const fs_drag *drags, int n_drags, int
         FS_CUDA_TRY(cudaMemcpyAsync(p_out, d_p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
     if (div_out)
         FS_CUDA_TRY(cudaMemcpyAsync(div_out, d_div, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out));
-    FS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_c_in, 0));
-    if ((e = core_advect_rgb(ctx, (fs_rgb_uq32 *)d_c2, (fs_rgb_uq32 *)d_c, (fs_vec2f *)d_v, g, dt, 0, nullptr)))
-        return e;
-    D2H(c, d_c2, n * sizeof(fs_rgb_uq32));
+    if (bands == 1) {
+        FS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_band_in[0], 0));
+        if ((e = core_advect_rgb(ctx, (fs_rgb_uq32 *)d_c2, (fs_rgb_uq32 *)d_c, (fs_vec2f *)d_v, g, dt, 0, nullptr)))
+            return e;
+        D2H(c, d_c2, n * sizeof(fs_rgb_uq32));
+        FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        FS_CUDA_TRY(cudaStreamSynchronize(ctx->copy_out));
+        return FS_OK;
+    }
+    FS_CUDA_TRY(cudaMemsetAsync(ctx->band_flag_dev, 0, sizeof(int), ctx->stream));
+    for (int b = 0; b < bands; b++) {
+        const int have = b + 1 < bands ? b + 1 : bands - 1;            // last band that must have arrived
+        FS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_band_in[have], 0));
+        Geo gb = g;
+        gb.y0 = row0[b];
+        gb.y1 = row0[b + 1];
+        gb.vy1 = row0[have + 1];
+        if ((e = core_advect_rgb(ctx, (fs_rgb_uq32 *)d_c2, (fs_rgb_uq32 *)d_c, (fs_vec2f *)d_v, gb, dt, 0,
+                                 ctx->band_flag_dev)))
+            return e;
+        FS_CUDA_TRY(cudaEventRecord(ctx->ev_band_done[b], ctx->stream));
+        FS_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_band_done[b], 0));
+        FS_CUDA_TRY(cudaMemcpyAsync((char *)c + row0[b] * row_c, (const char *)d_c2 + row0[b] * row_c,
+                                    (row0[b + 1] - row0[b]) * row_c, cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    int flag = 0;
+    FS_CUDA_TRY(cudaMemcpyAsync(&flag, ctx->band_flag_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     FS_CUDA_TRY(cudaStreamSynchronize(ctx->copy_out));
+    if (flag) {
+        ctx->stat_e2e_redos++;
+        if ((e = core_advect_rgb(ctx, (fs_rgb_uq32 *)d_c2, (fs_rgb_uq32 *)d_c, (fs_vec2f *)d_v, g, dt, 0, nullptr)))
+            return e;
+        D2H(c, d_c2, n * sizeof(fs_rgb_uq32));
+        FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
     return FS_OK;
 }
 

@@ -9,6 +9,7 @@
 using namespace fs;
 
 constexpr int WORK_SLOTS = 64;
+constexpr int E2E_MAX_BANDS = 16;
 enum Scratch { S_VTMP = 0, S_CTMP, S_DIV, S_P, S_P2, S_HV, S_HV2, S_HC, S_HC2, S_HP, S_HD, S_HIMG, S_EDRAG, S_ECNT, S_ECTMP, S_SOLVE_FLAGS, S_COUNT };
 
 struct fs_ctx {
@@ -27,6 +28,10 @@ struct fs_ctx {
     int *rim_dev;               // WORK_SLOTS rim-tile counters of the fused SOR + halo-exchange pass
     cudaStream_t copy_in, copy_out;   // side streams of fsh_step: PCIe copies overlap the compute
     cudaEvent_t ev_start, ev_c_in, ev_v_done;
+    cudaEvent_t ev_band_in[E2E_MAX_BANDS], ev_band_done[E2E_MAX_BANDS];   // fsh_step's dye bands: arrived / advected
+    int *band_flag_dev;         // raised when a dye backtrace of fsh_step reached a band that had not arrived yet
+    int opt_e2e_bands;          // row bands the dye of fsh_step travels in (1 = one piece)
+    int stat_e2e_redos;         // fsh_step calls whose banded dye advect had to be redone in one piece
     size_t max_smem_optin;
     unsigned int solve_gen;     // generation stamp of the single-launch solve's completion flags
     int opt_sor_one_launch;

@@ -85,6 +85,11 @@ int  fs_ctx_synchronize(fs_ctx *ctx);
  *              0 = one kernel per operator; default 5
  *   "sor_grid_limit": cap on the persistent SOR grid, 0 (default) = one CTA per SM; used when several
  *              emulated ranks share one device
+ *   "e2e_bands": row bands the dye of fsh_step travels in, 1..16 (default 8; fewer when the grid has
+ *              under 128 rows per band): band b is advected and sent home once bands 0..b+1 have
+ *              arrived, so both PCIe directions stay busy.  A backtrace that reaches a band still
+ *              in flight is detected and the dye advect redone in one piece ("e2e_redos",
+ *              read-only, counts those calls)
  *   "num_sms": (read-only) SMs of the context's device */
 int  fs_ctx_set_option(fs_ctx *ctx, const char *name, int value);
 int  fs_ctx_get_option(fs_ctx *ctx, const char *name, int *value);

@@ -297,6 +297,33 @@ def test_host_pointer_dropins(ctx, oracle):
     assert_bit_equal(img, oracle.upscale4_rgb565(c), "fsh upscale")
 
 
+@pytest.mark.parametrize("bands,vx,expect_redo", [(8, None, False), (3, None, False), (1, None, False),
+                                                   (8, -30000.0, True), (8, 30000.0, None)])
+def test_host_pointer_step_dye_bands(ctx, oracle, bands, vx, expect_redo):
+    """fsh_step sends the dye up and down in row bands (band b is advected once bands 0..b+1 arrived).  A drag
+    fast enough to backtrace DOWN across more than a band (30000 nodes/s * dt = 1000 rows) must trip the
+    valid-rectangle flag and be redone in one piece; the same drag pointing up reaches bands that are
+    already there (what the projection does to its neighbours is not pinned down).  Same bits every way."""
+    dim_x, dim_y = 128, 1024
+    v, c = rand_fields(31, dim_x, dim_y, 40.0)
+    dr = rand_drags(32, dim_x, dim_y, 6)
+    if vx is not None:
+        dr["cx"] = np.minimum(dr["cx"], 300)                  # in the first bands, far from the bottom wall
+        dr["vx"] = vx                                         # .vx drives the row (j) axis, ino:266
+    ctx.set_option("e2e_bands", bands)
+    redos = ctx.get_option("e2e_redos")
+    try:
+        hv, hc = v.copy(), c.copy()
+        ctx.step(hv, hc, dr, dim_x, dim_y, DT, 1.0, 8, 1.96)
+    finally:
+        ctx.set_option("e2e_bands", 8)
+    ov, oc = oracle.step(v.copy(), c.copy(), dr, DT, 1.0, 8, 1.96)
+    assert_bit_equal(hv, ov, f"fsh step v ({bands} bands)")
+    assert_bit_equal(hc, oc, f"fsh step dye ({bands} bands)")
+    if expect_redo is not None:
+        assert ctx.get_option("e2e_redos") - redos == int(expect_redo)
+
+
 def test_invalid_arguments(ctx):
     import esp32_fluid_simulation_b200 as fb
     v = torch.zeros(4, 4, 2, device="cuda")
