@@ -39,7 +39,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--ensemble", type=int, default=0, help="batch size: bench the smem-resident ensemble kernel instead")
     ap.add_argument("--ens-shape", default="80x60")
-    ap.add_argument("--ens-variant", type=int, default=1)
+    ap.add_argument("--ens-variant", default="0", help="comma-separated values of option 'ensemble' to time")
     args = ap.parse_args()
     nx, ny = args.n, args.ny or args.n
     nodes = nx * ny
@@ -143,18 +143,19 @@ def bench_ensemble(args, ctx, stream, peak):
         c = torch.randint(0, 2 ** 31 - 1, (batch, dim_y, dim_x, 3), device="cuda", dtype=torch.int32, generator=g)
     stream.synchronize()
     rows = []
-    ctx.set_option("ensemble", args.ens_variant)
-    for n_steps in (1, 4, 16):
-        ms = timeit(stream, lambda: ctx.ensemble_step(v, c, batch, dim_x, dim_y, synth.DT, 1.0, iters, 1.96, n_steps),
-                    reps=3, warm=1)
-        cells = batch * n * n_steps
-        r = {"kernel": f"ensemble_step[{dim_x}x{dim_y} x{batch}, K={iters}, n_steps={n_steps}]", "ms": round(ms, 3),
-             "mcell_steps_per_s": round(cells / (ms * 1e-3) / 1e6, 1),
-             "grid_steps_per_s": round(batch * n_steps / (ms * 1e-3), 1),
-             "hbm_GBps_state_io": round(batch * n * 40 / (ms * 1e-3) / 1e9, 1),
-             "smem_bytes_per_cta": 40 * n}
-        rows.append(r)
-        print(json.dumps(r), flush=True)
+    for variant in (int(x) for x in str(args.ens_variant).split(",")):
+        ctx.set_option("ensemble", variant)
+        for n_steps in (1, 16):
+            ms = timeit(stream, lambda: ctx.ensemble_step(v, c, batch, dim_x, dim_y, synth.DT, 1.0, iters, 1.96, n_steps),
+                        reps=3, warm=1)
+            cells = batch * n * n_steps
+            r = {"kernel": f"ensemble_step[{dim_x}x{dim_y} x{batch}, K={iters}, n_steps={n_steps}, variant={variant}]",
+                 "ms": round(ms, 3),
+                 "mcell_steps_per_s": round(cells / (ms * 1e-3) / 1e6, 1),
+                 "grid_steps_per_s": round(batch * n_steps / (ms * 1e-3), 1),
+                 "hbm_GBps_state_io": round(batch * n * 40 / (ms * 1e-3) / 1e9, 1)}
+            rows.append(r)
+            print(json.dumps(r), flush=True)
     if args.out:
         json.dump({"rows": rows}, open(args.out, "w"), indent=1)
 

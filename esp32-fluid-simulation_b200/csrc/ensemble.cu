@@ -20,52 +20,12 @@
 // one node of each red/black colour, so in every half-sweep each thread updates
 // exactly one node of each of its pairs.  (i,j) of a thread's pairs are computed
 // once per grid and kept in registers.
-#include "advect.cuh"
+#include "ensemble_reg.cuh"
 #include "kernels.h"
-#include "sor.cuh"
 
 namespace fs {
 
 constexpr int ENS_MAX_NODES = 6144;     // 2 nodes x threads x pairs per thread of every variant below
-
-template <class P>
-struct SmemFetch {
-    const typename P::raw_t *base;
-    int dim_x;
-    __device__ __forceinline__ void operator()(int gi, int gj, typename P::raw_t (&o)[P::NC]) const
-    {
-        const typename P::raw_t *q = base + (gj * dim_x + gi) * P::NC;
-#pragma unroll
-        for (int ch = 0; ch < P::NC; ch++) o[ch] = q[ch];
-    }
-};
-
-// dye of one grid in global memory.  Plain (L1-cached) loads: every dye word is a corner of ~4
-// backtraces, and going to L2 for each of them cost 10x the grid's bytes in L2 traffic (measured:
-// the whole step 55 % slower).  The previous step's result was written by this very CTA — ordered
-// by the __syncthreads between the steps (CTA scope) — so only the read-only (ld.global.nc) path
-// must not be used.
-struct DyeFetch {
-    const uint32_t *base;
-    int dim_x;
-    __device__ __forceinline__ void operator()(int gi, int gj, uint32_t (&o)[3]) const
-    {
-        const uint32_t *q = base + (size_t)(gj * dim_x + gi) * 3;
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) o[ch] = q[ch];
-    }
-};
-
-struct EnsArgs {
-    float2 *v;
-    uint32_t *c;
-    uint32_t *scratch;      // [gridDim.x][3N]: per-CTA dye ping-pong slot
-    const fs_drag *drags;   // device: [n_steps][batch][max_drags]
-    const int *counts;      // device: [n_steps][batch]
-    int max_drags, batch, dim_x, dim_y, iters, n_steps;
-    float dt, two_dx_inv;
-    SorCoef k;
-};
 
 // ENS_MAX_THREADS x MINB = CTA size limit and CTAs per SM the kernel is compiled for; ENS_MAX_ROUNDS =
 // node pairs per thread
@@ -294,6 +254,20 @@ __global__ void __launch_bounds__(ENS_MAX_THREADS, MINB) ensemble_kernel(const E
     }
 }
 
+// ---- second generation: projection in registers (ensemble_reg.cuh) -------------------------------------
+struct EnsEnvDevice {
+    int tid, nthreads, block, nblocks;
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+
+template <int R, int MAXT, bool DYE_SMEM>
+__global__ void __launch_bounds__(MAXT, 1) ensemble_reg_kernel(const EnsArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const EnsEnvDevice env{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
+    ens_reg_body<R, DYE_SMEM>(a, smem_raw, env);
+}
+
 size_t ensemble_scratch_bytes(int dim_x, int dim_y, int grid) { return (size_t)grid * dim_x * dim_y * 12; }
 
 size_t ensemble_smem_bytes(int dim_x, int dim_y, bool dye_smem)
@@ -301,14 +275,13 @@ size_t ensemble_smem_bytes(int dim_x, int dim_y, bool dye_smem)
     return (size_t)(dye_smem ? 40 : 16) * dim_x * dim_y + 16;
 }
 
-// variant 0 (default): dye in shared memory while 40 B/node fit one CTA, else streamed; 1/2/3: streamed dye, two
-// CTAs per SM; 4: streamed dye, one CTA per SM
+// first-generation kernel — variant 0: dye in shared memory while 40 B/node fit one CTA, else streamed; 1/2/3:
+// streamed dye, two CTAs per SM; 4: streamed dye, one CTA per SM
 static bool ens_dye_smem(int dim_x, int dim_y, int variant)
 {
     return variant == 0 && ensemble_smem_bytes(dim_x, dim_y, true) <= 227 * 1024 &&
            (dim_x * dim_y + 1) / 2 <= 1024 * 3;
 }
-
 
 bool ensemble_supported(int dim_x, int dim_y, size_t max_smem_optin)
 {
@@ -316,12 +289,89 @@ bool ensemble_supported(int dim_x, int dim_y, size_t max_smem_optin)
     return dim_x < 65536 && dim_y < 32768 && n <= ENS_MAX_NODES && (size_t)(16 * n + 16) <= max_smem_optin;
 }
 
+// What a call runs.  Option "ensemble" (ctx->opt_ens): 0 = automatic (the register-tiled kernel, falling back
+// to the first generation for shapes it does not take); 1-4 = first generation with streamed dye (see above),
+// 5 = first generation, automatic; 6/7/8/9 = register-tiled with R = 2/4/6/8 rows per thread; 12/14/16/18 =
+// the same with the dye streamed through L1/L2 instead of held in shared memory.
+struct EnsPlan {
+    bool reg;          // register-tiled kernel
+    int R;             // rows per thread
+    bool dye_smem;
+    int threads;
+    size_t smem;
+    int old_variant;   // first generation: its variant number
+};
+constexpr int ENS_REG_DEFAULT_R = 2;
+constexpr size_t ENS_SMEM_LIMIT = 227 * 1024;
+
+static int ens_reg_maxt(int R) { return R == 2 ? 768 : R == 4 ? 512 : R == 6 ? 384 : 256; }
+
+static bool ens_reg_plan(EnsPlan &pl, int dim_x, int dim_y, int R, bool want_dye_smem)
+{
+    if (dim_x < 2 || dim_y < 2) return false;          // sample_interior needs a cell to clamp to
+    const int ns = ens_reg_blocks(dim_x, dim_y, R);
+    int threads = (ns + 31) / 32 * 32;
+    if (threads < 64) threads = 64;
+    if (threads > ens_reg_maxt(R)) return false;
+    pl.reg = true;
+    pl.R = R;
+    pl.threads = threads;
+    pl.dye_smem = want_dye_smem && ens_reg_smem_bytes(dim_x, dim_y, R, true) <= ENS_SMEM_LIMIT;
+    pl.smem = ens_reg_smem_bytes(dim_x, dim_y, R, pl.dye_smem);
+    pl.old_variant = 0;
+    return pl.smem <= ENS_SMEM_LIMIT;
+}
+
+static EnsPlan ens_plan(int dim_x, int dim_y, int variant)
+{
+    EnsPlan pl{};
+    if (variant == 0) {
+        // fewest rows per thread that fit a CTA starting from the default: more threads hide the advects' latency
+        for (int R = ENS_REG_DEFAULT_R; R <= 8; R += 2)
+            if (ens_reg_plan(pl, dim_x, dim_y, R, true)) return pl;
+    } else if (variant >= 6 && variant <= 9) {
+        if (ens_reg_plan(pl, dim_x, dim_y, 2 * (variant - 5), true)) return pl;
+    } else if (variant >= 12 && variant <= 18 && variant % 2 == 0) {
+        if (ens_reg_plan(pl, dim_x, dim_y, variant - 10, false)) return pl;
+    }
+    pl = EnsPlan{};
+    pl.old_variant = (variant >= 1 && variant <= 4) ? variant : 0;
+    return pl;
+}
+
+template <int R, int MAXT, bool DYE_SMEM>
+static int ens_reg_occupancy(const EnsPlan &pl, int *per_sm)
+{
+    cudaError_t e = cudaFuncSetAttribute(ensemble_reg_kernel<R, MAXT, DYE_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, ensemble_reg_kernel<R, MAXT, DYE_SMEM>, pl.threads, pl.smem);
+}
+
+template <bool DYE_SMEM>
+static int ens_reg_occupancy_r(const EnsPlan &pl, int *per_sm)
+{
+    switch (pl.R) {
+        case 2: return ens_reg_occupancy<2, 768, DYE_SMEM>(pl, per_sm);
+        case 4: return ens_reg_occupancy<4, 512, DYE_SMEM>(pl, per_sm);
+        case 6: return ens_reg_occupancy<6, 384, DYE_SMEM>(pl, per_sm);
+        default: return ens_reg_occupancy<8, 256, DYE_SMEM>(pl, per_sm);
+    }
+}
+
 int ensemble_grid(int batch, int dim_x, int dim_y, int num_sms, int variant)
 {
-    // persistent CTAs walking the batch: one per SM, or two when the variant streams the dye and 2 x 16N bytes fit
+    const EnsPlan pl = ens_plan(dim_x, dim_y, variant);
     int per_sm = 1;
-    if (!ens_dye_smem(dim_x, dim_y, variant) && variant != 4 && ensemble_smem_bytes(dim_x, dim_y, false) * 2 + 2048 <= 227 * 1024)
+    if (pl.reg) {
+        // persistent CTAs walking the batch, as many per SM as registers and shared memory allow
+        const int e = pl.dye_smem ? ens_reg_occupancy_r<true>(pl, &per_sm) : ens_reg_occupancy_r<false>(pl, &per_sm);
+        if (e != 0 || per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;
+    } else if (!ens_dye_smem(dim_x, dim_y, pl.old_variant) && pl.old_variant != 4 &&
+               ensemble_smem_bytes(dim_x, dim_y, false) * 2 + 2048 <= 227 * 1024) {
+        // first generation: one per SM, or two when the variant streams the dye and 2 x 16N bytes fit
         per_sm = 2;
+    }
     return batch < per_sm * num_sms ? batch : per_sm * num_sms;
 }
 
@@ -342,6 +392,27 @@ static int launch_ens(const Launch &L, const EnsArgs &a, int grid, int threads_o
     return (int)cudaGetLastError();
 }
 
+template <int R, int MAXT, bool DYE_SMEM>
+static int launch_ens_reg(const Launch &L, const EnsArgs &a, const EnsPlan &pl, int grid)
+{
+    cudaError_t e = cudaFuncSetAttribute(ensemble_reg_kernel<R, MAXT, DYE_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return (int)e;
+    ensemble_reg_kernel<R, MAXT, DYE_SMEM><<<grid, pl.threads, pl.smem, L.stream>>>(a);
+    ++*L.launches;
+    return (int)cudaGetLastError();
+}
+
+template <bool DYE_SMEM>
+static int launch_ens_reg_r(const Launch &L, const EnsArgs &a, const EnsPlan &pl, int grid)
+{
+    switch (pl.R) {
+        case 2: return launch_ens_reg<2, 768, DYE_SMEM>(L, a, pl, grid);
+        case 4: return launch_ens_reg<4, 512, DYE_SMEM>(L, a, pl, grid);
+        case 6: return launch_ens_reg<6, 384, DYE_SMEM>(L, a, pl, grid);
+        default: return launch_ens_reg<8, 256, DYE_SMEM>(L, a, pl, grid);
+    }
+}
+
 int launch_ensemble(const Launch &L, float2 *v, uint32_t *c, uint32_t *scratch, const fs_drag *drags_dev,
                     const int *counts_dev, int max_drags, int batch, int dim_x, int dim_y, float dt,
                     float dx, int iters, float omega, int n_steps, int variant)
@@ -354,8 +425,10 @@ int launch_ensemble(const Launch &L, float2 *v, uint32_t *c, uint32_t *scratch, 
     a.two_dx_inv = 1.0f / (2.0f * dx);
     a.k = make_sor_coef(dx, omega);
     const int grid = ensemble_grid(batch, dim_x, dim_y, L.num_sms, variant);
-    if (ens_dye_smem(dim_x, dim_y, variant)) return launch_ens<1024, 1, 3, true>(L, a, grid, 0);   // everything resident
-    switch (variant) {
+    const EnsPlan pl = ens_plan(dim_x, dim_y, variant);
+    if (pl.reg) return pl.dye_smem ? launch_ens_reg_r<true>(L, a, pl, grid) : launch_ens_reg_r<false>(L, a, pl, grid);
+    if (ens_dye_smem(dim_x, dim_y, pl.old_variant)) return launch_ens<1024, 1, 3, true>(L, a, grid, 0);   // everything resident
+    switch (pl.old_variant) {
         case 1: return launch_ens<512, 2, 6, false>(L, a, grid, 0);       // two grids per SM, 6 pairs per thread
         case 2: return launch_ens<512, 2, 6, false>(L, a, grid, 512);     // two grids per SM, 16 warps each
         case 3: return launch_ens<512, 2, 6, false>(L, a, grid, 384);     // two grids per SM, 12 warps each

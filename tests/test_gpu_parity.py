@@ -381,9 +381,14 @@ def test_4096_size_independent_properties(ctx):
 
 @pytest.mark.parametrize("shape,iters,batch,n_steps", [((61, 81), 10, 5, 1), ((80, 60), 10, 300, 3), ((60, 80), 7, 4, 2),
                                                        ((7, 3), 4, 3, 2), ((2, 2), 3, 2, 1), ((64, 90), 10, 2, 1)])
-def test_ensemble_step(ctx, oracle, shape, iters, batch, n_steps):
+@pytest.mark.parametrize("variant", [0, 5, 6, 7, 8, 9, 14])
+def test_ensemble_step(ctx, oracle, shape, iters, batch, n_steps, variant):
+    """variant = option "ensemble": 0 automatic (register-tiled projection, ensemble_reg.cuh), 5 the
+    first-generation kernel, 6-9 register-tiled with 2/4/6/8 rows per thread, 14 = 4 rows, dye streamed."""
     from esp32_fluid_simulation_b200 import synth
     dim_x, dim_y = shape
+    if variant not in (0, 5) and batch > 8:
+        batch = 149 + variant          # (more grids than CTAs for every variant without repeating the big case 7 times)
     max_drags = 4
     v = np.stack([synth.velocity(dim_x, dim_y, seed=100 + b, vmax=90.0) for b in range(batch)])
     c = np.stack([synth.dye(dim_x, dim_y, seed=200 + b, n_splats=6) for b in range(batch)])
@@ -395,7 +400,11 @@ def test_ensemble_step(ctx, oracle, shape, iters, batch, n_steps):
             counts[s, b] = k
             drags[s, b, :k] = synth.drags(dim_x, dim_y, s * 1000 + b, n=max_drags, vmax=300.0)[:k]
     dv, dc = to_dev(v), to_dev(c)
-    ctx.ensemble_step(dv, dc, batch, dim_x, dim_y, DT, 1.0, iters, 1.96, n_steps, drags, counts, max_drags)
+    ctx.set_option("ensemble", variant)
+    try:
+        ctx.ensemble_step(dv, dc, batch, dim_x, dim_y, DT, 1.0, iters, 1.96, n_steps, drags, counts, max_drags)
+    finally:
+        ctx.set_option("ensemble", 0)
     gv, gc = to_host(dv), to_host(dc, np.uint32)
     check = range(batch) if batch <= 8 else [0, 1, 147, 148, 149, batch - 1]
     for b in check:

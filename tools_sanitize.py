@@ -37,7 +37,7 @@ for dim_x, dim_y, iters in ((256, 224, 10), (61, 81, 6)):
 bv = torch.from_numpy(np.stack([synth.velocity(80, 60, seed=b) for b in range(3)])).cuda()
 bc = torch.from_numpy(np.stack([synth.dye(80, 60, seed=b, n_splats=4) for b in range(3)]).view(np.int32)).cuda()
 ctx.ensemble_step(bv, bc, 3, 80, 60, synth.DT, 1.0, 4, 1.96, 2)
-for variant in (1, 4):                                  # streamed-dye variants of the ensemble kernel
+for variant in (1, 4, 5, 6, 7, 8, 9, 12, 14):           # first-generation variants, register-tiled R = 2..8, streamed dye
     ctx.set_option("ensemble", variant)
     ctx.ensemble_step(bv, bc, 3, 80, 60, synth.DT, 1.0, 4, 1.96, 3)
 ctx.set_option("ensemble", 0)
