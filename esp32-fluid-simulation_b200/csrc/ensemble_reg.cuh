@@ -55,21 +55,23 @@ __host__ __device__ static inline size_t ens_reg_smem_bytes(int dim_x, int dim_y
 }
 
 // Interior case of sample<T> (advect.h:38-42) on a cell clamped into the grid: no branches, so the loads of
-// several nodes overlap.  Returns true when the backtrace left [0, GX-1) x [0, GY-1) (the same tests as
-// sample(), advect.h:26-29) — the caller then redoes the node through sample().  Needs GX, GY >= 2.
+// several nodes overlap.  Returns true when the backtrace left [0, GX-1) x [0, GY-1) (equivalent to the tests
+// of sample(), advect.h:26-29) — the caller then redoes the node through sample().  Needs GX, GY >= 2.
 template <class P, class Fetch>
 __device__ __forceinline__ bool sample_interior(typename P::raw_t (&out)[P::NC], const Fetch &fetch, float i, float j,
-                                                int GX, int GY)
+                                                float gx2, float gy2)     // (float)(GX - 2), (float)(GY - 2)
 {
     using raw_t = typename P::raw_t;
     constexpr int NC = P::NC;
-    const bool oob = i < 0.0f || i >= (float)(GX - 1) || j < 0.0f || j >= (float)(GY - 1);
     const float i_floor = floorf(i), j_floor = floorf(j);
     const float di = __fsub_rn(i, i_floor), dj = __fsub_rn(j, j_floor);
     const float wi = __fsub_rn(1.0f, di), wj = __fsub_rn(1.0f, dj);
     // clamp in float first: the float -> int conversion of a huge value is only defined on the device
-    const float ci = fminf(fmaxf(i_floor, 0.0f), (float)(GX - 2)), cj = fminf(fmaxf(j_floor, 0.0f), (float)(GY - 2));
-    const int gi = (int)ci, gj = (int)cj;     // (a NaN passes fmaxf as 0, like the device's cvt.rzi of a NaN)
+    const float ci = fminf(fmaxf(i_floor, 0.0f), gx2), cj = fminf(fmaxf(j_floor, 0.0f), gy2);
+    // 0 <= i < GX-1  <=>  0 <= floor(i) <= GX-2  <=>  the clamp left floor(i) alone.  (A NaN passes fmaxf as 0 and
+    // compares unequal: it is redone by sample(), which takes the same cell (0, .) through cvt.rzi.)
+    const bool oob = ci != i_floor || cj != j_floor;
+    const int gi = (int)ci, gj = (int)cj;
     raw_t p11[NC], p12[NC], p21[NC], p22[NC];
     fetch(gi, gj, p11);
     fetch(gi, gj + 1, p12);
@@ -166,6 +168,7 @@ __device__ __forceinline__ void ens_reg_body(const EnsArgs &a, unsigned char *sm
     uint32_t *C2 = DYE_SMEM ? C1 + 3 * (size_t)N : a.scratch + (size_t)env.block * N * 3;
 
     const bool ragged = (dim_x & 3) != 0 || dim_y % R != 0;   // some blocks reach beyond the grid
+    const bool even_x = (dim_x & 1) == 0;                     // block rows start 16-byte aligned
     // ---- this thread's block: columns i0..i0+3, rows j0..j0+R-1 ------------------------------------
     const bool act = tid < NS;
     const int s = act ? tid / CG : 0, g = act ? tid - s * CG : 0;
@@ -193,8 +196,10 @@ __device__ __forceinline__ void ens_reg_body(const EnsArgs &a, unsigned char *sm
     // mailboxes (word offsets into the dead velocity buffer); a missing neighbour is the block of zeros
     const int o_zero = NS * MS;
     const int o_mine = tid * MS;
-    const int o_left = g > 0 ? o_mine - MS : o_zero, o_right = g < CG - 1 ? o_mine + MS : o_zero;
-    const int o_down = s > 0 ? o_mine - CG * MS : o_zero, o_up = s < RS - 1 ? o_mine + CG * MS : o_zero;
+    int o_left = g > 0 ? o_mine - MS : o_zero, o_right = g < CG - 1 ? o_mine + MS : o_zero;
+    int o_down = s > 0 ? o_mine - CG * MS : o_zero, o_up = s < RS - 1 ? o_mine + CG * MS : o_zero;
+    // (kept in registers: recomputing them cost ~25 integer instructions in every half-sweep)
+    FS_OPAQUE_REG(o_left); FS_OPAQUE_REG(o_right); FS_OPAQUE_REG(o_down); FS_OPAQUE_REG(o_up);
     // neighbours of the block in the velocity array, clamped so that every address is inside the buffer
     const int row_dn = s > 0 ? row[0] - dim_x : row[0];
     const int row_up = min(j0 + R, dim_y - 1) * dim_x + i0;
@@ -203,7 +208,9 @@ __device__ __forceinline__ void ens_reg_body(const EnsArgs &a, unsigned char *sm
     // 16-byte copies between global and shared memory need N % 4 == 0 (12N and 8N multiples of 16) and aligned arrays
     const bool vec16 = (N & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.v) | reinterpret_cast<uintptr_t>(a.c)) & 15) == 0;
     // ---- node-strided mapping of the advects ----------------------------------------------------------
-    const int adv_di = NT % dim_x, adv_dj = NT / dim_x, adv_i0 = tid % dim_x, adv_j0 = tid / dim_x;
+    // (coordinates kept as floats: exact for these sizes, and the backtrace wants them as floats)
+    const float adv_di = (float)(NT % dim_x), adv_dj = (float)(NT / dim_x), adv_i0 = (float)(tid % dim_x), adv_j0 = (float)(tid / dim_x);
+    const float fdim_x = (float)dim_x, gx2 = (float)(dim_x - 2), gy2 = (float)(dim_y - 2);
 
     for (int grid = env.block; grid < a.batch; grid += env.nblocks) {
         // ---- load the grid's state ---------------------------------------------------------------------
@@ -243,7 +250,7 @@ __device__ __forceinline__ void ens_reg_body(const EnsArgs &a, unsigned char *sm
             // ---- advect velocity, no-slip (ino:253): A -> B -----------------------------------------------
             {
                 SmemFetch<Vec2Payload> fetch{reinterpret_cast<const float *>(A), dim_x};
-                int i = adv_i0, j = adv_j0;
+                float fi = adv_i0, fj = adv_j0;             // node coordinates as floats (exact), advect.h:81
                 for (int nb = tid; nb < N; nb += U * NT) {
                     float res[U][2];
                     float si[U], sj[U];
@@ -251,18 +258,20 @@ __device__ __forceinline__ void ens_reg_body(const EnsArgs &a, unsigned char *sm
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         const int n = min(nb + u * NT, N - 1);      // (clamped: the surplus lanes recompute the last node)
-                        backtrace(si[u], sj[u], i, j, A[n], a.dt);
-                        oob[u] = sample_interior<Vec2Payload>(res[u], fetch, si[u], sj[u], dim_x, dim_y);
-                        if (nb + u * NT < N) {
-                            i += adv_di;
-                            j += adv_dj;
-                            if (i >= dim_x) { i -= dim_x; j++; }
-                        }
+                        const float2 vel = A[n];
+                        si[u] = __fsub_rn(fi, __fmul_rn(vel.x, a.dt));
+                        sj[u] = __fsub_rn(fj, __fmul_rn(vel.y, a.dt));
+                        oob[u] = sample_interior<Vec2Payload>(res[u], fetch, si[u], sj[u], gx2, gy2);
+                        fi += adv_di;
+                        fj += adv_dj;
+                        if (fi >= fdim_x) { fi -= fdim_x; fj += 1.0f; }
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        if (oob[u]) sample<Vec2Payload>(res[u], fetch, si[u], sj[u], dim_x, dim_y, true);
-                        if (nb + u * NT < N) B[nb + u * NT] = make_float2(res[u][0], res[u][1]);
+                        if (nb + u * NT < N) {
+                            if (oob[u]) sample<Vec2Payload>(res[u], fetch, si[u], sj[u], dim_x, dim_y, true);
+                            B[nb + u * NT] = make_float2(res[u][0], res[u][1]);
+                        }
                     }
                 }
             }
@@ -287,21 +296,42 @@ __device__ __forceinline__ void ens_reg_body(const EnsArgs &a, unsigned char *sm
             if (act) {
                 // divergence (ino:274, finitediff.cpp:9-39) of the block from B and its one-node ring
                 float vx[R][4], vy[R][4], xl[R], xr[R], yd[4], yu[4];
+                if (even_x) {
+                    // dim_x even: every row of the block starts 16-byte aligned, two nodes per load
 #pragma unroll
-                for (int r = 0; r < R; r++) {
+                    for (int r = 0; r < R; r++) {
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const float4 t = *reinterpret_cast<const float4 *>(B + row[r] + 2 * h);
+                            vx[r][2 * h] = t.x; vy[r][2 * h] = t.y; vx[r][2 * h + 1] = t.z; vy[r][2 * h + 1] = t.w;
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const float4 td = *reinterpret_cast<const float4 *>(B + row_dn + 2 * h);
+                        const float4 tu = *reinterpret_cast<const float4 *>(B + row_up + 2 * h);
+                        yd[2 * h] = td.y; yd[2 * h + 1] = td.w; yu[2 * h] = tu.y; yu[2 * h + 1] = tu.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            const float2 t = B[row[r] + c];
+                            vx[r][c] = t.x;
+                            vy[r][c] = t.y;
+                        }
+                    }
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
-                        const float2 t = B[row[r] + c];
-                        vx[r][c] = t.x;
-                        vy[r][c] = t.y;
+                        yd[c] = B[row_dn + c].y;
+                        yu[c] = B[row_up + c].y;
                     }
-                    xl[r] = B[row[r] + off_l].x;
-                    xr[r] = B[row[r] + 4].x;
                 }
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    yd[c] = B[row_dn + c].y;
-                    yu[c] = B[row_up + c].y;
+                for (int r = 0; r < R; r++) {
+                    xl[r] = B[row[r] + off_l].x;
+                    xr[r] = B[row[r] + 4].x;
                 }
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -354,6 +384,7 @@ __device__ __forceinline__ void ens_reg_body(const EnsArgs &a, unsigned char *sm
                 }
 #pragma unroll
                 for (int r = 0; r < R; r++) {
+                    float gx[4], gy[4];                    // (p_right - p_left) / 2dx, (p_up - p_down) / 2dx
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
                         const int i = i0 + c, j = j0 + r;
@@ -362,11 +393,31 @@ __device__ __forceinline__ void ens_reg_body(const EnsArgs &a, unsigned char *sm
                         const float pr = i < dim_x - 1 ? (c < 3 ? p[r][c < 3 ? c + 1 : 3] : hr[r]) : pc;
                         const float pd = j > 0 ? (r > 0 ? p[r > 0 ? r - 1 : 0][c] : vd[c]) : pc;
                         const float pu = j < dim_y - 1 ? (r < R - 1 ? p[r < R - 1 ? r + 1 : R - 1][c] : vu[c]) : pc;
-                        if (cm[c] & rm[r]) {
-                            float2 c0 = B[row[r] + c];
-                            c0.x = __fsub_rn(c0.x, __fmul_rn(__fsub_rn(pr, pl), a.two_dx_inv));
-                            c0.y = __fsub_rn(c0.y, __fmul_rn(__fsub_rn(pu, pd), a.two_dx_inv));
-                            B[row[r] + c] = c0;
+                        gx[c] = __fmul_rn(__fsub_rn(pr, pl), a.two_dx_inv);
+                        gy[c] = __fmul_rn(__fsub_rn(pu, pd), a.two_dx_inv);
+                    }
+                    if (even_x) {
+                        // dim_x even: nodes are inside the grid in pairs, 16 bytes per access
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            if (cm[2 * h] & rm[r]) {
+                                float4 t = *reinterpret_cast<const float4 *>(B + row[r] + 2 * h);
+                                t.x = __fsub_rn(t.x, gx[2 * h]);
+                                t.y = __fsub_rn(t.y, gy[2 * h]);
+                                t.z = __fsub_rn(t.z, gx[2 * h + 1]);
+                                t.w = __fsub_rn(t.w, gy[2 * h + 1]);
+                                *reinterpret_cast<float4 *>(B + row[r] + 2 * h) = t;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            if (cm[c] & rm[r]) {
+                                float2 c0 = B[row[r] + c];
+                                c0.x = __fsub_rn(c0.x, gx[c]);
+                                c0.y = __fsub_rn(c0.y, gy[c]);
+                                B[row[r] + c] = c0;
+                            }
                         }
                     }
                 }
@@ -375,7 +426,7 @@ __device__ __forceinline__ void ens_reg_body(const EnsArgs &a, unsigned char *sm
             // ---- advect dye, free-slip sampling (ino:282) with the projected velocity: C1 -> C2 ---------------
             {
                 DyeFetch fetch{C1, dim_x};
-                int i = adv_i0, j = adv_j0;
+                float fi = adv_i0, fj = adv_j0;
                 for (int nb = tid; nb < N; nb += U * NT) {
                     uint32_t res[U][3];
                     float si[U], sj[U];
@@ -383,19 +434,19 @@ __device__ __forceinline__ void ens_reg_body(const EnsArgs &a, unsigned char *sm
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         const int n = min(nb + u * NT, N - 1);
-                        backtrace(si[u], sj[u], i, j, B[n], a.dt);
-                        oob[u] = sample_interior<RgbPayload>(res[u], fetch, si[u], sj[u], dim_x, dim_y);
-                        if (nb + u * NT < N) {
-                            i += adv_di;
-                            j += adv_dj;
-                            if (i >= dim_x) { i -= dim_x; j++; }
-                        }
+                        const float2 vel = B[n];
+                        si[u] = __fsub_rn(fi, __fmul_rn(vel.x, a.dt));
+                        sj[u] = __fsub_rn(fj, __fmul_rn(vel.y, a.dt));
+                        oob[u] = sample_interior<RgbPayload>(res[u], fetch, si[u], sj[u], gx2, gy2);
+                        fi += adv_di;
+                        fj += adv_dj;
+                        if (fi >= fdim_x) { fi -= fdim_x; fj += 1.0f; }
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        if (oob[u]) sample<RgbPayload>(res[u], fetch, si[u], sj[u], dim_x, dim_y, false);
                         const int n = nb + u * NT;
                         if (n < N) {
+                            if (oob[u]) sample<RgbPayload>(res[u], fetch, si[u], sj[u], dim_x, dim_y, false);
                             C2[3 * n + 0] = res[u][0];
                             C2[3 * n + 1] = res[u][1];
                             C2[3 * n + 2] = res[u][2];
