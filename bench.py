@@ -452,8 +452,10 @@ def bench_single(args, fb, synth, torch):
                                          "state_io_GBps": eb * ex * ey * 40 / (t_ms * 1e-3) / 1e9}
         extra["ensemble"] = {"workload": f"{eb} independent {ex}x{ey} grids, K={ek}, one CTA per grid, state resident in "
                                          "shared memory (BASELINE.json configs[1])", "results": ens,
-                             "bound": "instruction issue / shared memory (profiles/r02_ncu_ensemble*.json), not HBM: "
-                                      "state I/O is 40 B/node per CALL"}
+                             "kernel": "ensemble_reg_kernel<2,640,1> (csrc/ensemble_reg.cuh): projection in registers, "
+                                       "4x2-node block per thread, rim values through per-thread mailboxes",
+                             "bound": "instruction issue 62 % / shared-memory wavefronts 65 % (profiles/"
+                                      "r02_ncu_ensemble_reg_r2*.json), not HBM: state I/O is 40 B/node per CALL"}
         del ev, ec
     except Exception as e:  # noqa: BLE001 — never let an extra take the headline down
         extra["ensemble"] = {"error": f"{type(e).__name__}: {e}"}

@@ -1,6 +1,8 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "ensemble" 2>&1 | tail -5
-timeout 300 python bench_kernels.py --ensemble 65536 --ens-shape 80x60 --ens-variant 0,7,12 --out gpurun_out/r02_ens_sweep3.json 2>&1 | tail -20
-timeout 200 python bench_kernels.py --ensemble 16384 --ens-shape 61x81 --ens-variant 0,7 --out gpurun_out/r02_ens_sweep3_61x81.json 2>&1 | tail -10
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:ensemble_reg --launch-skip 4 -c 1 -f -o gpurun_out/ens_reg_r2_16steps_b python bench_kernels.py --ensemble 8192 --ens-variant 0 2>&1 | tail -3
+( time timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 ) 2>&1
+timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_n1_now.json 2> gpurun_out/bench_n1_now.err; tail -c 600 gpurun_out/bench_n1_now.err; python -c "
+import json
+d=json.loads(open('gpurun_out/bench_n1_now.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['ms'], d['extra']['ensemble'], d['cpu_baseline'])
+"
