@@ -185,16 +185,22 @@ advect_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     // while the tile is in flight: velocities (dye advect) for this thread's nodes
     constexpr int ROWS_PER_IT = AT_THREADS / AT_TX, ITERS = AT_TY / ROWS_PER_IT;
     const int cx = threadIdx.x % AT_TX, cy = threadIdx.x / AT_TX;
+    // per-thread invariants of the row loop (ncu: per-iteration rectangle tests, int -> float conversions of the
+    // node coordinates and 64-bit index arithmetic were ~10 of ~76 instructions per node)
+    const int lx = tx0 + cx;
+    const bool live_x = lx < g.x1;
+    const size_t l0 = (size_t)(ty0 + cy) * g.nx + lx, lstep = (size_t)ROWS_PER_IT * g.nx;
+    const float fgi = (float)(g.ox + lx);                   // node coordinates as floats: exact
     float2 vel[ITERS];
     if (!a.vel_is_p) {
 #pragma unroll
         for (int it = 0; it < ITERS; it++) {
-            const int lx = tx0 + cx, ly = ty0 + cy + it * ROWS_PER_IT;
-            const bool live = lx < g.x1 && ly < g.y1;
-            vel[it] = live ? __ldg(a.vel + (size_t)ly * g.nx + lx) : make_float2(0.f, 0.f);
+            const int ly = ty0 + cy + it * ROWS_PER_IT;
+            const bool live = live_x && ly < g.y1;
+            vel[it] = live ? __ldg(a.vel + l0 + it * lstep) : make_float2(0.f, 0.f);
             if (a.grad_p && live) {
                 vel[it] = grad_sub_value(vel[it], a.grad_p, g, lx, ly, a.two_dx_inv);
-                a.v_out[(size_t)ly * g.nx + lx] = vel[it];
+                a.v_out[l0 + it * lstep] = vel[it];
             }
         }
     }
@@ -204,11 +210,12 @@ advect_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                        g.vx0, g.vy0, g.vx1 - g.vx0, g.vy1 - g.vy0, a.status};
     const FastWindow fw = fast_window<P::NC>(g, bx0, by0, TS::W, TS::H);
     const raw_t *ftile = tile + fw.toff;
+    const float fgj0 = (float)(g.oy + ty0 + cy);
 #pragma unroll
     for (int it = 0; it < ITERS; it++) {
         const int ry = cy + it * ROWS_PER_IT;
-        const int lx = tx0 + cx, ly = ty0 + ry;
-        const bool live = lx < g.x1 && ly < g.y1;
+        const int ly = ty0 + ry;
+        const bool live = live_x && ly < g.y1;
         Raw<P> out;
 #pragma unroll
         for (int ch = 0; ch < P::NC; ch++) out.v[ch] = 0;
@@ -222,9 +229,11 @@ advect_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             } else {
                 vv = vel[it];
             }
-            float si, sj, di, dj;
+            float di, dj;
             int tx, ty;
-            backtrace(si, sj, g.ox + lx, g.oy + ly, vv, a.dt);
+            // advect.h:81 (backtrace()) with the node coordinates already in float
+            const float si = __fsub_rn(fgi, __fmul_rn(vv.x, a.dt));
+            const float sj = __fsub_rn(fgj0 + (float)(it * ROWS_PER_IT), __fmul_rn(vv.y, a.dt));
             // interior (advect.h:38: !x_oob && !y_oob) with all four corners staged: straight-line path
             if (fast_cell(fw, si, sj, tx, ty, di, dj)) {
                 const float wi = __fsub_rn(1.0f, di), wj = __fsub_rn(1.0f, dj);
@@ -250,13 +259,13 @@ advect_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             }
         }
         if constexpr (P::NC == 2) {
-            if (live) reinterpret_cast<float2 *>(a.next_p)[(size_t)ly * g.nx + lx] = make_float2(out.v[0], out.v[1]);
+            if (live) reinterpret_cast<float2 *>(a.next_p)[l0 + it * lstep] = make_float2(out.v[0], out.v[1]);
         } else if constexpr (STORE_TMA) {
             raw_t *q = otile + (ry * AT_TX + cx) * 3;
             q[0] = out.v[0]; q[1] = out.v[1]; q[2] = out.v[2];
         } else {
             if (live) {
-                raw_t *q = reinterpret_cast<raw_t *>(a.next_p) + ((size_t)ly * g.nx + lx) * 3;
+                raw_t *q = reinterpret_cast<raw_t *>(a.next_p) + (l0 + it * lstep) * 3;
                 q[0] = out.v[0]; q[1] = out.v[1]; q[2] = out.v[2];
             }
         }
@@ -387,6 +396,30 @@ advect_div_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_c
     // ---- forced velocity + its divergence for the tile ----
     constexpr int ROWS_PER_IT = AT_THREADS / AT_TX, ITERS = AT_TY / ROWS_PER_IT;
     const int cx = threadIdx.x % AT_TX, cy = threadIdx.x / AT_TX;
+    // CTA-uniform: a whole tile inside the compute and store rectangles that touches no global wall takes the
+    // interior expression (div_expr_fast, finitediff.cpp:9-17) with no per-node tests and running pointers
+    // (ncu: the general loop below spent ~56 instructions per node on rectangle / wall tests and 64-bit
+    // address arithmetic, a third of the kernel)
+    const bool whole = tx0 + AT_TX <= g.x1 && ty0 + AT_TY <= g.y1 && tx0 >= a.sx0 && tx0 + AT_TX <= a.sx1 &&
+                       ty0 >= a.sy0 && ty0 + AT_TY <= a.sy1 && g.ox + tx0 > 0 && g.ox + tx0 + AT_TX < g.GX &&
+                       g.oy + ty0 > 0 && g.oy + ty0 + AT_TY < g.GY;
+    if (whole) {
+        const float2 *ap = adv + (cy + 1) * AD_AW + cx + 1;
+        const size_t l0 = (size_t)(ty0 + cy) * g.nx + tx0 + cx, lstep = (size_t)ROWS_PER_IT * g.nx;
+        float2 *vo = a.v_out + l0;
+        float *dv = a.div + l0;
+#pragma unroll
+        for (int it = 0; it < ITERS; it++) {
+            const float2 c = ap[0];
+            const float s = __fadd_rn(__fadd_rn(-ap[-1].x, ap[1].x), __fadd_rn(-ap[-AD_AW].y, ap[AD_AW].y));
+            *vo = c;
+            *dv = __fmul_rn(s, a.two_dx_inv);
+            ap += ROWS_PER_IT * AD_AW;
+            vo += lstep;
+            dv += lstep;
+        }
+        return;
+    }
 #pragma unroll
     for (int it = 0; it < ITERS; it++) {
         const int ry = cy + it * ROWS_PER_IT;

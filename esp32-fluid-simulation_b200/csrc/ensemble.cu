@@ -304,7 +304,9 @@ struct EnsPlan {
 constexpr int ENS_REG_DEFAULT_R = 2;
 constexpr size_t ENS_SMEM_LIMIT = 227 * 1024;
 
-static int ens_reg_maxt(int R) { return R == 2 ? 640 : R == 4 ? 512 : R == 6 ? 384 : 256; }
+// R = 2 is compiled twice: up to 20 warps (5 per SM sub-partition: 96 registers) and up to 21 (6 on one
+// sub-partition: 80 registers) — 61x81, the reference's own grid, needs 656 threads
+static int ens_reg_maxt(int R) { return R == 2 ? 672 : R == 4 ? 512 : R == 6 ? 384 : 256; }
 
 static bool ens_reg_plan(EnsPlan &pl, int dim_x, int dim_y, int R, bool want_dye_smem)
 {
@@ -351,7 +353,7 @@ template <bool DYE_SMEM>
 static int ens_reg_occupancy_r(const EnsPlan &pl, int *per_sm)
 {
     switch (pl.R) {
-        case 2: return ens_reg_occupancy<2, 640, DYE_SMEM>(pl, per_sm);
+        case 2: return pl.threads <= 640 ? ens_reg_occupancy<2, 640, DYE_SMEM>(pl, per_sm) : ens_reg_occupancy<2, 672, DYE_SMEM>(pl, per_sm);
         case 4: return ens_reg_occupancy<4, 512, DYE_SMEM>(pl, per_sm);
         case 6: return ens_reg_occupancy<6, 384, DYE_SMEM>(pl, per_sm);
         default: return ens_reg_occupancy<8, 256, DYE_SMEM>(pl, per_sm);
@@ -406,7 +408,7 @@ template <bool DYE_SMEM>
 static int launch_ens_reg_r(const Launch &L, const EnsArgs &a, const EnsPlan &pl, int grid)
 {
     switch (pl.R) {
-        case 2: return launch_ens_reg<2, 640, DYE_SMEM>(L, a, pl, grid);
+        case 2: return pl.threads <= 640 ? launch_ens_reg<2, 640, DYE_SMEM>(L, a, pl, grid) : launch_ens_reg<2, 672, DYE_SMEM>(L, a, pl, grid);
         case 4: return launch_ens_reg<4, 512, DYE_SMEM>(L, a, pl, grid);
         case 6: return launch_ens_reg<6, 384, DYE_SMEM>(L, a, pl, grid);
         default: return launch_ens_reg<8, 256, DYE_SMEM>(L, a, pl, grid);
