@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--ensemble", type=int, default=0, help="batch size: bench the smem-resident ensemble kernel instead")
     ap.add_argument("--ens-shape", default="80x60")
     ap.add_argument("--ens-variant", default="0", help="comma-separated values of option 'ensemble' to time")
+    ap.add_argument("--ens-steps", default="1,16", help="comma-separated steps per call")
     args = ap.parse_args()
     nx, ny = args.n, args.ny or args.n
     nodes = nx * ny
@@ -145,7 +146,7 @@ def bench_ensemble(args, ctx, stream, peak):
     rows = []
     for variant in (int(x) for x in str(args.ens_variant).split(",")):
         ctx.set_option("ensemble", variant)
-        for n_steps in (1, 16):
+        for n_steps in (int(x) for x in args.ens_steps.split(",")):
             ms = timeit(stream, lambda: ctx.ensemble_step(v, c, batch, dim_x, dim_y, synth.DT, 1.0, iters, 1.96, n_steps),
                         reps=3, warm=1)
             cells = batch * n * n_steps

@@ -256,6 +256,8 @@ __global__ void __launch_bounds__(ENS_MAX_THREADS, MINB) ensemble_kernel(const E
 
 // ---- second generation: projection in registers (ensemble_reg.cuh) -------------------------------------
 struct EnsEnvDevice {
+    static constexpr bool kAsync = true;     // bulk-copy pipeline available
+    static constexpr bool kEmulatePipe = false;
     int tid, nthreads, block, nblocks;
     __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
@@ -265,7 +267,8 @@ __global__ void __launch_bounds__(MAXT, 1) ensemble_reg_kernel(const EnsArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const EnsEnvDevice env{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
-    ens_reg_body<R, DYE_SMEM>(a, smem_raw, env);
+    // the pipelined flow keeps 8 dye results per thread in registers: only the 96-register build of R = 2 has room
+    ens_reg_body<R, DYE_SMEM, EnsEnvDevice, (R == 2 && MAXT <= 640)>(a, smem_raw, env);
 }
 
 size_t ensemble_scratch_bytes(int dim_x, int dim_y, int grid) { return (size_t)grid * dim_x * dim_y * 12; }
@@ -292,7 +295,8 @@ bool ensemble_supported(int dim_x, int dim_y, size_t max_smem_optin)
 // What a call runs.  Option "ensemble" (ctx->opt_ens): 0 = automatic (the register-tiled kernel, falling back
 // to the first generation for shapes it does not take); 1-4 = first generation with streamed dye (see above),
 // 5 = first generation, automatic; 6/7/8/9 = register-tiled with R = 2/4/6/8 rows per thread; 12/14/16/18 =
-// the same with the dye streamed through L1/L2 instead of held in shared memory.
+// the same with the dye streamed through L1/L2 instead of held in shared memory; 20 / 21 = automatic with the
+// pipelined flow of the dye-resident R = 2 kernel forced on / off (default: on for calls of up to 6 steps).
 struct EnsPlan {
     bool reg;          // register-tiled kernel
     int R;             // rows per thread
@@ -302,6 +306,7 @@ struct EnsPlan {
     int old_variant;   // first generation: its variant number
 };
 constexpr int ENS_REG_DEFAULT_R = 2;
+constexpr int ENS_PIPE_MAX_STEPS = 6;    // measured crossover (80x60, K=10: 5.79 n + 0.30 ms against 5.55 n + 1.88 ms per call of n steps)
 constexpr size_t ENS_SMEM_LIMIT = 227 * 1024;
 
 // R = 2 is compiled twice: up to 20 warps (5 per SM sub-partition: 96 registers) and up to 21 (6 on one
@@ -362,6 +367,7 @@ static int ens_reg_occupancy_r(const EnsPlan &pl, int *per_sm)
 
 int ensemble_grid(int batch, int dim_x, int dim_y, int num_sms, int variant)
 {
+    if (variant == 20 || variant == 21) variant = 0;
     const EnsPlan pl = ens_plan(dim_x, dim_y, variant);
     int per_sm = 1;
     if (pl.reg) {
@@ -424,6 +430,9 @@ int launch_ensemble(const Launch &L, float2 *v, uint32_t *c, uint32_t *scratch, 
     a.v = v; a.c = c; a.scratch = scratch; a.drags = drags_dev; a.counts = counts_dev;
     a.max_drags = max_drags; a.batch = batch; a.dim_x = dim_x; a.dim_y = dim_y;
     a.iters = iters; a.n_steps = n_steps; a.dt = dt;
+    // variants 20 / 21: automatic plan with the pipelined flow forced on / off (measurement)
+    a.pipe_max_steps = variant == 20 ? 0x7fffffff : variant == 21 ? 0 : ENS_PIPE_MAX_STEPS;
+    if (variant == 20 || variant == 21) variant = 0;
     a.two_dx_inv = 1.0f / (2.0f * dx);
     a.k = make_sor_coef(dx, omega);
     const int grid = ensemble_grid(batch, dim_x, dim_y, L.num_sms, variant);

@@ -46,6 +46,7 @@ struct EnsArgs {
     const fs_drag *drags;   // device: [n_steps][batch][max_drags]
     const int *counts;      // device: [n_steps][batch]
     int max_drags, batch, dim_x, dim_y, iters, n_steps;
+    int pipe_max_steps;     // register-tiled, dye-resident kernel: calls of up to this many steps take the pipelined flow
     float dt, two_dx_inv;
     SorCoef k;
 };

@@ -29,6 +29,9 @@
 #pragma once
 
 #include "ensemble_common.cuh"
+#ifdef __CUDACC__
+#include "tma.cuh"
+#endif
 
 namespace fs {
 
@@ -51,7 +54,8 @@ __host__ __device__ static inline size_t ens_reg_vbuf_bytes(int dim_x, int dim_y
 }
 __host__ __device__ static inline size_t ens_reg_smem_bytes(int dim_x, int dim_y, int R, bool dye_smem)
 {
-    return 2 * ens_reg_vbuf_bytes(dim_x, dim_y, R) + (dye_smem ? (size_t)24 * dim_x * dim_y : 0);
+    // dye resident: two dye buffers and two mbarriers (the bulk-copy pipeline of ens_reg_body_resident)
+    return 2 * ens_reg_vbuf_bytes(dim_x, dim_y, R) + (dye_smem ? (size_t)24 * dim_x * dim_y + 16 : 0);
 }
 
 // Interior case of sample<T> (advect.h:38-42) on a cell clamped into the grid: no branches, so the loads of
@@ -149,338 +153,646 @@ __device__ __forceinline__ void ens_sor(float (&p)[R][4], const float (&d)[R][4]
 }
 
 // keeps the compiler from turning `x & mask` back into the comparison the mask came from (two selects and a
-// compare per use instead of one 3-input logic op)
+// compare per use instead of one 3-input logic op), and from rematerialising an offset in every half-sweep
 #define FS_OPAQUE_REG(x) asm volatile("" : "+r"(x))
 
-// Env: { int tid, nthreads, block, nblocks; void sync() const; }
-template <int R, bool DYE_SMEM, class Env>
-__device__ __forceinline__ void ens_reg_body(const EnsArgs &a, unsigned char *smem_raw, const Env &env)
-{
-    constexpr int MS = EnsRegLayout<R>::MAIL_STRIDE;
-    constexpr int U = R == 2 ? 2 : 4;                      // nodes per thread in flight in the advects (R = 2: 80 registers)
-    const int tid = env.tid, NT = env.nthreads;
-    const int dim_x = a.dim_x, dim_y = a.dim_y, N = dim_x * dim_y;
-    const int CG = (dim_x + 3) >> 2, RS = (dim_y + R - 1) / R, NS = CG * RS;
-    const size_t vbuf = ens_reg_vbuf_bytes(dim_x, dim_y, R);
-    float2 *A = reinterpret_cast<float2 *>(smem_raw);
-    float2 *B = reinterpret_cast<float2 *>(smem_raw + vbuf);
-    uint32_t *C1 = DYE_SMEM ? reinterpret_cast<uint32_t *>(smem_raw + 2 * vbuf) : nullptr;
-    uint32_t *C2 = DYE_SMEM ? C1 + 3 * (size_t)N : a.scratch + (size_t)env.block * N * 3;
-
-    const bool ragged = (dim_x & 3) != 0 || dim_y % R != 0;   // some blocks reach beyond the grid
-    const bool even_x = (dim_x & 1) == 0;                     // block rows start 16-byte aligned
-    // ---- this thread's block: columns i0..i0+3, rows j0..j0+R-1 ------------------------------------
-    const bool act = tid < NS;
-    const int s = act ? tid / CG : 0, g = act ? tid - s * CG : 0;
-    const int i0 = 4 * g, j0 = R * s;
+// Everything a thread knows about its place in the CTA: its 4 x R block for the projection, its mailbox
+// neighbours, its node-strided walk for the advects.
+template <int R>
+struct EnsMap {
+    int tid, NT, dim_x, dim_y, N, CG, RS, NS;
+    bool ragged;          // some blocks reach beyond the grid
+    bool even_x;          // block rows start 16-byte aligned
+    bool act;             // this thread owns a block
+    int s, g, i0, j0;
     unsigned cm[4], rm[R];
     float coef[R][4];
-    int row[R];                                            // node index of (i0, j0 + r), row clamped into the grid
+    int row[R];           // node index of (i0, j0 + r), row clamped into the grid
+    int o_zero, o_mine, o_left, o_right, o_down, o_up;   // mailboxes (word offsets into the dead velocity buffer)
+    int row_dn, row_up, off_l;                           // the block's ring in the velocity array, clamped into the buffer
+    float adv_di, adv_dj, adv_i0, adv_j0, fdim_x, gx2, gy2;   // node-strided mapping of the advects, as floats (exact)
+};
+
+template <int R>
+__device__ __forceinline__ void ens_map_init(EnsMap<R> &m, const EnsArgs &a, int tid, int NT)
+{
+    constexpr int MS = EnsRegLayout<R>::MAIL_STRIDE;
+    const int dim_x = a.dim_x, dim_y = a.dim_y;
+    m.tid = tid; m.NT = NT; m.dim_x = dim_x; m.dim_y = dim_y; m.N = dim_x * dim_y;
+    m.CG = (dim_x + 3) >> 2; m.RS = (dim_y + R - 1) / R; m.NS = m.CG * m.RS;
+    m.ragged = (dim_x & 3) != 0 || dim_y % R != 0;
+    m.even_x = (dim_x & 1) == 0;
+    m.act = tid < m.NS;
+    m.s = m.act ? tid / m.CG : 0;
+    m.g = m.act ? tid - m.s * m.CG : 0;
+    m.i0 = 4 * m.g; m.j0 = R * m.s;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-        cm[c] = i0 + c < dim_x ? 0xffffffffu : 0u;
-        FS_OPAQUE_REG(cm[c]);
+        m.cm[c] = m.i0 + c < dim_x ? 0xffffffffu : 0u;
+        FS_OPAQUE_REG(m.cm[c]);
     }
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        rm[r] = j0 + r < dim_y ? 0xffffffffu : 0u;
-        FS_OPAQUE_REG(rm[r]);
-        row[r] = min(j0 + r, dim_y - 1) * dim_x + i0;
+        m.rm[r] = m.j0 + r < dim_y ? 0xffffffffu : 0u;
+        FS_OPAQUE_REG(m.rm[r]);
+        m.row[r] = min(m.j0 + r, dim_y - 1) * dim_x + m.i0;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const int i = i0 + c, j = j0 + r;
+            const int i = m.i0 + c, j = m.j0 + r;
             const int nb = 4 - (i == 0) - (i == dim_x - 1) - (j == 0) - (j == dim_y - 1);
-            coef[r][c] = nb == 4 ? a.k.neg_quarter : nb == 3 ? a.k.neg_third : a.k.neg_half;
+            m.coef[r][c] = nb == 4 ? a.k.neg_quarter : nb == 3 ? a.k.neg_third : a.k.neg_half;
         }
     }
-    // mailboxes (word offsets into the dead velocity buffer); a missing neighbour is the block of zeros
-    const int o_zero = NS * MS;
-    const int o_mine = tid * MS;
-    int o_left = g > 0 ? o_mine - MS : o_zero, o_right = g < CG - 1 ? o_mine + MS : o_zero;
-    int o_down = s > 0 ? o_mine - CG * MS : o_zero, o_up = s < RS - 1 ? o_mine + CG * MS : o_zero;
+    // a missing neighbour thread is the block of zeros
+    m.o_zero = m.NS * MS;
+    m.o_mine = tid * MS;
+    m.o_left = m.g > 0 ? m.o_mine - MS : m.o_zero;
+    m.o_right = m.g < m.CG - 1 ? m.o_mine + MS : m.o_zero;
+    m.o_down = m.s > 0 ? m.o_mine - m.CG * MS : m.o_zero;
+    m.o_up = m.s < m.RS - 1 ? m.o_mine + m.CG * MS : m.o_zero;
     // (kept in registers: recomputing them cost ~25 integer instructions in every half-sweep)
-    FS_OPAQUE_REG(o_left); FS_OPAQUE_REG(o_right); FS_OPAQUE_REG(o_down); FS_OPAQUE_REG(o_up);
-    // neighbours of the block in the velocity array, clamped so that every address is inside the buffer
-    const int row_dn = s > 0 ? row[0] - dim_x : row[0];
-    const int row_up = min(j0 + R, dim_y - 1) * dim_x + i0;
-    const int off_l = g > 0 ? -1 : 0;
+    FS_OPAQUE_REG(m.o_left); FS_OPAQUE_REG(m.o_right); FS_OPAQUE_REG(m.o_down); FS_OPAQUE_REG(m.o_up);
+    m.row_dn = m.s > 0 ? m.row[0] - dim_x : m.row[0];
+    m.row_up = min(m.j0 + R, dim_y - 1) * dim_x + m.i0;
+    m.off_l = m.g > 0 ? -1 : 0;
+    m.adv_di = (float)(NT % dim_x); m.adv_dj = (float)(NT / dim_x);
+    m.adv_i0 = (float)(tid % dim_x); m.adv_j0 = (float)(tid / dim_x);
+    m.fdim_x = (float)dim_x; m.gx2 = (float)(dim_x - 2); m.gy2 = (float)(dim_y - 2);
+}
 
-    // 16-byte copies between global and shared memory need N % 4 == 0 (12N and 8N multiples of 16) and aligned arrays
-    const bool vec16 = (N & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.v) | reinterpret_cast<uintptr_t>(a.c)) & 15) == 0;
-    // ---- node-strided mapping of the advects ----------------------------------------------------------
-    // (coordinates kept as floats: exact for these sizes, and the backtrace wants them as floats)
-    const float adv_di = (float)(NT % dim_x), adv_dj = (float)(NT / dim_x), adv_i0 = (float)(tid % dim_x), adv_j0 = (float)(tid / dim_x);
-    const float fdim_x = (float)dim_x, gx2 = (float)(dim_x - 2), gy2 = (float)(dim_y - 2);
-
-    for (int grid = env.block; grid < a.batch; grid += env.nblocks) {
-        // ---- load the grid's state ---------------------------------------------------------------------
-        const float2 *gv = a.v + (size_t)grid * N;
-        uint32_t *user_c = a.c + (size_t)grid * N * 3;
-        if (vec16) {
-            // 16 bytes per load: four times the bytes in flight per thread (the phase is latency-bound)
-            const uint4 *src = reinterpret_cast<const uint4 *>(gv);
-            uint4 *dst = reinterpret_cast<uint4 *>(A);
-            for (int n = tid; n < N / 2; n += NT) dst[n] = __ldg(src + n);
-        } else {
-            for (int n = tid; n < N; n += NT) A[n] = __ldg(gv + n);
+// ---- advect velocity, no-slip (ino:253): A -> B ------------------------------------------------------------
+template <int R, int U>
+__device__ __forceinline__ void ens_advect_velocity(const EnsMap<R> &m, const EnsArgs &a, const float2 *A, float2 *B)
+{
+    const int N = m.N, NT = m.NT;
+    SmemFetch<Vec2Payload> fetch{reinterpret_cast<const float *>(A), m.dim_x};
+    float fi = m.adv_i0, fj = m.adv_j0;             // node coordinates as floats (exact), advect.h:81
+    for (int nb = m.tid; nb < N; nb += U * NT) {
+        float res[U][2];
+        float si[U], sj[U];
+        bool oob[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int n = min(nb + u * NT, N - 1);      // (clamped: the surplus lanes recompute the last node)
+            const float2 vel = A[n];
+            si[u] = __fsub_rn(fi, __fmul_rn(vel.x, a.dt));
+            sj[u] = __fsub_rn(fj, __fmul_rn(vel.y, a.dt));
+            oob[u] = sample_interior<Vec2Payload>(res[u], fetch, si[u], sj[u], m.gx2, m.gy2);
+            fi += m.adv_di;
+            fj += m.adv_dj;
+            if (fi >= m.fdim_x) { fi -= m.fdim_x; fj += 1.0f; }
         }
-        if constexpr (DYE_SMEM) {
-            if (vec16) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(user_c);
-                uint4 *dst = reinterpret_cast<uint4 *>(C1);
-                for (int n = tid; n < 3 * N / 4; n += NT) dst[n] = __ldg(src + n);
-            } else {
-                for (int n = tid; n < 3 * N; n += NT) C1[n] = __ldg(user_c + n);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (nb + u * NT < N) {
+                if (oob[u]) sample<Vec2Payload>(res[u], fetch, si[u], sj[u], m.dim_x, m.dim_y, true);
+                B[nb + u * NT] = make_float2(res[u][0], res[u][1]);
             }
-        } else {
-            C1 = user_c;
+        }
+    }
+}
+
+// ---- drags (ino:264-269): in order, one thread; ends in a barrier when there are records -------------------
+template <int R, class Env>
+__device__ __forceinline__ void ens_drags(const EnsMap<R> &m, const EnsArgs &a, float2 *B, int step, int grid, const Env &env)
+{
+    if (a.max_drags > 0) {
+        if (m.tid == 0) {
+            const size_t slot = (size_t)step * a.batch + grid;
+            const int cnt = min(a.counts[slot], a.max_drags);
+            const fs_drag *dr = a.drags + slot * a.max_drags;
+            for (int q = 0; q < cnt; q++) {
+                const fs_drag d = dr[q];
+                if (d.cy < m.dim_x && d.cx < m.dim_y) B[d.cx * m.dim_x + d.cy] = make_float2(d.vy, d.vx);
+            }
         }
         env.sync();
+    }
+}
 
+// ---- projection in registers (ino:274-276): divergence of B, red-black SOR, gradient subtracted from B in place.
+// `mail` = the velocity buffer that is dead now.  Ends BEFORE the barrier that publishes B.
+template <int R, class Env>
+__device__ __forceinline__ void ens_project(const EnsMap<R> &m, const EnsArgs &a, float *mail, float2 *B, const Env &env)
+{
+    constexpr int MS = EnsRegLayout<R>::MAIL_STRIDE;
+    const int dim_x = m.dim_x, dim_y = m.dim_y, i0 = m.i0, j0 = m.j0;
+    float p[R][4], d[R][4];
+    if (m.tid < MS) mail[m.o_zero + m.tid] = 0.0f;       // (first read after the first half-sweep's barrier)
+    if (m.act) {
+        // divergence (ino:274, finitediff.cpp:9-39) of the block from B and its one-node ring
+        float vx[R][4], vy[R][4], xl[R], xr[R], yd[4], yu[4];
+        if (m.even_x) {
+            // dim_x even: every row of the block starts 16-byte aligned, two nodes per load
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const float4 t = *reinterpret_cast<const float4 *>(B + m.row[r] + 2 * h);
+                    vx[r][2 * h] = t.x; vy[r][2 * h] = t.y; vx[r][2 * h + 1] = t.z; vy[r][2 * h + 1] = t.w;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const float4 td = *reinterpret_cast<const float4 *>(B + m.row_dn + 2 * h);
+                const float4 tu = *reinterpret_cast<const float4 *>(B + m.row_up + 2 * h);
+                yd[2 * h] = td.y; yd[2 * h + 1] = td.w; yu[2 * h] = tu.y; yu[2 * h + 1] = tu.w;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const float2 t = B[m.row[r] + c];
+                    vx[r][c] = t.x;
+                    vy[r][c] = t.y;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                yd[c] = B[m.row_dn + c].y;
+                yu[c] = B[m.row_up + c].y;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            xl[r] = B[m.row[r] + m.off_l].x;
+            xr[r] = B[m.row[r] + 4].x;
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int i = i0 + c, j = j0 + r;
+                const float xm = c > 0 ? vx[r][c > 0 ? c - 1 : 0] : xl[r], xp = c < 3 ? vx[r][c < 3 ? c + 1 : 3] : xr[r];
+                const float ym = r > 0 ? vy[r > 0 ? r - 1 : 0][c] : yd[c], yp = r < R - 1 ? vy[r < R - 1 ? r + 1 : R - 1][c] : yu[c];
+                const bool wall = i == 0 || i == dim_x - 1 || j == 0 || j == dim_y - 1;
+                float sd;
+                if (!wall) {
+                    sd = __fadd_rn(__fadd_rn(-xm, xp), __fadd_rn(-ym, yp));
+                } else {
+                    sd = 0.0f;
+                    sd = __fadd_rn(sd, i > 0 ? -xm : vx[r][c]);
+                    sd = __fadd_rn(sd, i < dim_x - 1 ? xp : -vx[r][c]);
+                    sd = __fadd_rn(sd, j > 0 ? -ym : vy[r][c]);
+                    sd = __fadd_rn(sd, j < dim_y - 1 ? yp : -vy[r][c]);
+                }
+                // dx*d: the same product every iteration (poisson.cpp:88,109)
+                const float dd = __fmul_rn(a.k.dx, __fmul_rn(sd, a.two_dx_inv));
+                d[r][c] = __uint_as_float(__float_as_uint(dd) & m.cm[c] & m.rm[r]);
+                p[r][c] = 0.0f;                    // poisson.cpp:117-119
+            }
+        }
+    }
+    // ---- red-black SOR (ino:275) ---------------------------------------------------------------------
+    if (a.iters > 0) {
+        if (m.ragged)
+            ens_sor<R, true>(p, d, m.coef, m.cm, m.rm, mail + m.o_mine, mail + m.o_left, mail + m.o_right, mail + m.o_down, mail + m.o_up, a.k, a.iters, m.act, env);
+        else
+            ens_sor<R, false>(p, d, m.coef, m.cm, m.rm, mail + m.o_mine, mail + m.o_left, mail + m.o_right, mail + m.o_down, mail + m.o_up, a.k, a.iters, m.act, env);
+    } else {
+        if (m.act)
+            for (int w = 0; w < MS; w++) mail[m.o_mine + w] = 0.0f;
+        env.sync();
+    }
+    // ---- subtract gradient (ino:276, finitediff.cpp:41-82), in place on B ----------------------------
+    if (m.act) {
+        float hl[R], hr[R], vd[4], vu[4];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            hl[r] = mail[m.o_left + 2 * r + 1];
+            hr[r] = mail[m.o_right + 2 * r + 0];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            vd[c] = mail[m.o_down + 2 * R + 4 + c];
+            vu[c] = mail[m.o_up + 2 * R + c];
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            float gx[4], gy[4];                    // (p_right - p_left) / 2dx, (p_up - p_down) / 2dx
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int i = i0 + c, j = j0 + r;
+                const float pc = p[r][c];
+                const float pl = i > 0 ? (c > 0 ? p[r][c > 0 ? c - 1 : 0] : hl[r]) : pc;
+                const float pr = i < dim_x - 1 ? (c < 3 ? p[r][c < 3 ? c + 1 : 3] : hr[r]) : pc;
+                const float pd = j > 0 ? (r > 0 ? p[r > 0 ? r - 1 : 0][c] : vd[c]) : pc;
+                const float pu = j < dim_y - 1 ? (r < R - 1 ? p[r < R - 1 ? r + 1 : R - 1][c] : vu[c]) : pc;
+                gx[c] = __fmul_rn(__fsub_rn(pr, pl), a.two_dx_inv);
+                gy[c] = __fmul_rn(__fsub_rn(pu, pd), a.two_dx_inv);
+            }
+            if (m.even_x) {
+                // dim_x even: nodes are inside the grid in pairs, 16 bytes per access
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    if (m.cm[2 * h] & m.rm[r]) {
+                        float4 t = *reinterpret_cast<const float4 *>(B + m.row[r] + 2 * h);
+                        t.x = __fsub_rn(t.x, gx[2 * h]);
+                        t.y = __fsub_rn(t.y, gy[2 * h]);
+                        t.z = __fsub_rn(t.z, gx[2 * h + 1]);
+                        t.w = __fsub_rn(t.w, gy[2 * h + 1]);
+                        *reinterpret_cast<float4 *>(B + m.row[r] + 2 * h) = t;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (m.cm[c] & m.rm[r]) {
+                        float2 c0 = B[m.row[r] + c];
+                        c0.x = __fsub_rn(c0.x, gx[c]);
+                        c0.y = __fsub_rn(c0.y, gy[c]);
+                        B[m.row[r] + c] = c0;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- advect dye, free-slip sampling (ino:282) with the projected velocity B: C1 -> C2 (distinct buffers) ----
+template <int R, int U, class Fetch>
+__device__ __forceinline__ void ens_advect_dye(const EnsMap<R> &m, const EnsArgs &a, const float2 *B, const Fetch &fetch, uint32_t *C2)
+{
+    const int N = m.N, NT = m.NT;
+    float fi = m.adv_i0, fj = m.adv_j0;
+    for (int nb = m.tid; nb < N; nb += U * NT) {
+        uint32_t res[U][3];
+        float si[U], sj[U];
+        bool oob[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int n = min(nb + u * NT, N - 1);
+            const float2 vel = B[n];
+            si[u] = __fsub_rn(fi, __fmul_rn(vel.x, a.dt));
+            sj[u] = __fsub_rn(fj, __fmul_rn(vel.y, a.dt));
+            oob[u] = sample_interior<RgbPayload>(res[u], fetch, si[u], sj[u], m.gx2, m.gy2);
+            fi += m.adv_di;
+            fj += m.adv_dj;
+            if (fi >= m.fdim_x) { fi -= m.fdim_x; fj += 1.0f; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int n = nb + u * NT;
+            if (n < N) {
+                if (oob[u]) sample<RgbPayload>(res[u], fetch, si[u], sj[u], m.dim_x, m.dim_y, false);
+                C2[3 * n + 0] = res[u][0];
+                C2[3 * n + 1] = res[u][1];
+                C2[3 * n + 2] = res[u][2];
+            }
+        }
+    }
+}
+
+// The same advect IN PLACE: every thread keeps the results of all its nodes (at most 4R: the CTA has at least one
+// thread per 4 x R block) in registers until the whole CTA has finished reading C, then writes them back — so the
+// second dye buffer is free to receive the NEXT grid's dye while this one is being stepped.
+template <int R, int U, class Env>
+__device__ __forceinline__ void ens_advect_dye_in_place(const EnsMap<R> &m, const EnsArgs &a, const float2 *B, uint32_t *C, const Env &env)
+{
+    constexpr int KN = 4 * R;
+    static_assert(KN % U == 0, "");
+    const int N = m.N, NT = m.NT;
+    SmemFetch<RgbPayload> fetch{C, m.dim_x};
+    uint32_t res[KN][3];
+    float fi = m.adv_i0, fj = m.adv_j0;
+#pragma unroll
+    for (int k0 = 0; k0 < KN; k0 += U) {
+        if (m.tid + k0 * NT < N) {
+            float si[U], sj[U];
+            bool oob[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int n = min(m.tid + (k0 + u) * NT, N - 1);
+                const float2 vel = B[n];
+                si[u] = __fsub_rn(fi, __fmul_rn(vel.x, a.dt));
+                sj[u] = __fsub_rn(fj, __fmul_rn(vel.y, a.dt));
+                oob[u] = sample_interior<RgbPayload>(res[k0 + u], fetch, si[u], sj[u], m.gx2, m.gy2);
+                fi += m.adv_di;
+                fj += m.adv_dj;
+                if (fi >= m.fdim_x) { fi -= m.fdim_x; fj += 1.0f; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (oob[u] && m.tid + (k0 + u) * NT < N) sample<RgbPayload>(res[k0 + u], fetch, si[u], sj[u], m.dim_x, m.dim_y, false);
+        }
+    }
+    env.sync();                                 // every corner has been read
+#pragma unroll
+    for (int k = 0; k < KN; k++) {
+        const int n = m.tid + k * NT;
+        if (n < N) {
+            C[3 * n + 0] = res[k][0];
+            C[3 * n + 1] = res[k][1];
+            C[3 * n + 2] = res[k][2];
+        }
+    }
+}
+
+// cooperative copies between global and shared memory: 16 bytes per access when everything is aligned, else 8 (the
+// velocity) or 4 (the dye).  BATCH loads are issued before the first store: the phase is latency-bound, what counts
+// is the bytes in flight per thread (a plain loop kept ONE load in flight).
+template <class T, int BATCH>
+__device__ __forceinline__ void ens_copy_batched(T *dst, const T *src, int cnt, int tid, int NT, bool from_global)
+{
+    for (int n = tid; n < cnt; n += BATCH * NT) {
+        T t[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {       // (index clamped, load unconditional: keeps t[] in registers)
+            const int k = min(n + u * NT, cnt - 1);
+            t[u] = from_global ? __ldg(src + k) : src[k];
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; u++)
+            if (n + u * NT < cnt) dst[n + u * NT] = t[u];
+    }
+}
+// words = 32-bit words to copy; wide8 = the data is a whole number of 8-byte elements, 8-byte aligned (velocity)
+__device__ __forceinline__ void ens_copy_in(void *dst_smem, const void *src_gmem, int words, bool vec16, bool wide8, int tid, int NT)
+{
+    if (vec16)
+        ens_copy_batched<uint4, 4>(reinterpret_cast<uint4 *>(dst_smem), reinterpret_cast<const uint4 *>(src_gmem), words / 4, tid, NT, true);
+    else if (wide8)
+        ens_copy_batched<uint2, 8>(reinterpret_cast<uint2 *>(dst_smem), reinterpret_cast<const uint2 *>(src_gmem), words / 2, tid, NT, true);
+    else
+        ens_copy_batched<uint32_t, 8>(reinterpret_cast<uint32_t *>(dst_smem), reinterpret_cast<const uint32_t *>(src_gmem), words, tid, NT, true);
+}
+__device__ __forceinline__ void ens_copy_out(void *dst_gmem, const void *src_smem, int words, bool vec16, bool wide8, int tid, int NT)
+{
+    if (vec16)
+        ens_copy_batched<uint4, 4>(reinterpret_cast<uint4 *>(dst_gmem), reinterpret_cast<const uint4 *>(src_smem), words / 4, tid, NT, false);
+    else if (wide8)
+        ens_copy_batched<uint2, 8>(reinterpret_cast<uint2 *>(dst_gmem), reinterpret_cast<const uint2 *>(src_smem), words / 2, tid, NT, false);
+    else
+        ens_copy_batched<uint32_t, 8>(reinterpret_cast<uint32_t *>(dst_gmem), reinterpret_cast<const uint32_t *>(src_smem), words, tid, NT, false);
+}
+
+#ifdef __CUDACC__
+// 1-D bulk copies (TMA) and their completion mechanisms
+__device__ __forceinline__ void ens_bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    mbar_expect_tx(bar, bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void ens_bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int PENDING>
+__device__ __forceinline__ void ens_bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+}
+__device__ __forceinline__ void ens_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void ens_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
+// Env: { int tid, nthreads, block, nblocks; void sync() const; static constexpr bool kAsync, kEmulatePipe; }
+//
+// Dye RESIDENT in shared memory (40 B/node: velocity x2, dye x2), state I/O at the grid boundaries: load, step
+// n_steps times (dye ping-pong between the two buffers, ino:286), store.  The next grid's state is pulled into L2
+// during the last step so that its load pays the L2 latency instead of HBM's.
+template <int R, class Env>
+__device__ __forceinline__ void ens_resident_sync(const EnsMap<R> &m, const EnsArgs &a, unsigned char *smem_raw, bool vec16,
+                                                  const Env &env)
+{
+    constexpr int U = R == 2 ? 2 : 4;                      // nodes per thread in flight in the advects
+    const int tid = m.tid, NT = m.NT, N = m.N;
+    const size_t vbuf = ens_reg_vbuf_bytes(m.dim_x, m.dim_y, R);
+    float2 *A = reinterpret_cast<float2 *>(smem_raw);
+    float2 *B = reinterpret_cast<float2 *>(smem_raw + vbuf);
+    uint32_t *C1 = reinterpret_cast<uint32_t *>(smem_raw + 2 * vbuf);
+    uint32_t *C2 = C1 + 3 * (size_t)N;
+    for (int grid = env.block; grid < a.batch; grid += env.nblocks) {
+        ens_copy_in(A, a.v + (size_t)grid * N, 2 * N, vec16, true, tid, NT);
+        ens_copy_in(C1, a.c + (size_t)grid * N * 3, 3 * N, vec16, false, tid, NT);
+        env.sync();
         for (int step = 0; step < a.n_steps; step++) {
-            // during the last step, pull the next grid's state into L2: its load phase then pays the L2
-            // latency instead of HBM's
             if (step == a.n_steps - 1 && grid + env.nblocks < a.batch) {
                 const char *nv = reinterpret_cast<const char *>(a.v + (size_t)(grid + env.nblocks) * N);
                 const char *nc = reinterpret_cast<const char *>(a.c + (size_t)(grid + env.nblocks) * N * 3);
                 for (int l = tid * 128; l < N * 8; l += NT * 128) prefetch_l2(nv + l);
-                if constexpr (DYE_SMEM)
-                    for (int l = tid * 128; l < N * 12; l += NT * 128) prefetch_l2(nc + l);
+                for (int l = tid * 128; l < N * 12; l += NT * 128) prefetch_l2(nc + l);
             }
-            // ---- advect velocity, no-slip (ino:253): A -> B -----------------------------------------------
-            {
-                SmemFetch<Vec2Payload> fetch{reinterpret_cast<const float *>(A), dim_x};
-                float fi = adv_i0, fj = adv_j0;             // node coordinates as floats (exact), advect.h:81
-                for (int nb = tid; nb < N; nb += U * NT) {
-                    float res[U][2];
-                    float si[U], sj[U];
-                    bool oob[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int n = min(nb + u * NT, N - 1);      // (clamped: the surplus lanes recompute the last node)
-                        const float2 vel = A[n];
-                        si[u] = __fsub_rn(fi, __fmul_rn(vel.x, a.dt));
-                        sj[u] = __fsub_rn(fj, __fmul_rn(vel.y, a.dt));
-                        oob[u] = sample_interior<Vec2Payload>(res[u], fetch, si[u], sj[u], gx2, gy2);
-                        fi += adv_di;
-                        fj += adv_dj;
-                        if (fi >= fdim_x) { fi -= fdim_x; fj += 1.0f; }
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        if (nb + u * NT < N) {
-                            if (oob[u]) sample<Vec2Payload>(res[u], fetch, si[u], sj[u], dim_x, dim_y, true);
-                            B[nb + u * NT] = make_float2(res[u][0], res[u][1]);
-                        }
-                    }
-                }
-            }
+            ens_advect_velocity<R, U>(m, a, A, B);
             env.sync();
-            // ---- drags (ino:264-269): in order, one thread -----------------------------------------------
-            if (a.max_drags > 0) {
+            ens_drags(m, a, B, step, grid, env);
+            ens_project(m, a, reinterpret_cast<float *>(A), B, env);
+            env.sync();
+            ens_advect_dye<R, U>(m, a, B, SmemFetch<RgbPayload>{C1, m.dim_x}, C2);
+            env.sync();
+            // pointer swaps of ino:255 and ino:286
+            uint32_t *tc = C1; C1 = C2; C2 = tc;
+            float2 *tv = A; A = B; B = tv;
+        }
+        ens_copy_out(a.v + (size_t)grid * N, A, 2 * N, vec16, true, tid, NT);
+        ens_copy_out(a.c + (size_t)grid * N * 3, C1, 3 * N, vec16, false, tid, NT);
+        env.sync();
+    }
+}
+
+// The same with the state I/O OFF the critical path.  In a grid's LAST step the dye is advected in place, so the other
+// dye buffer is free from the start of that step: it receives the next grid's dye.  The next grid's velocity lands in
+// the dead velocity buffer during that step's dye advect, while this grid's projected velocity is already on its way
+// out; this grid's dye leaves while the next grid's first advect runs.  On the device (`async`: arrays 16-byte
+// aligned, N % 4 == 0) the copies are 1-D bulk copies (cp.async.bulk, SASS UBLKCP) issued by thread 0 and tracked by two
+// mbarriers / bulk groups; in the host emulation (Env::kEmulatePipe) the same copies are made cooperatively at the
+// same program points.
+template <int R, class Env>
+__device__ __forceinline__ void ens_resident_pipelined(const EnsMap<R> &m, const EnsArgs &a, unsigned char *smem_raw, bool vec16,
+                                                       bool async, const Env &env)
+{
+    constexpr int U = R == 2 ? 2 : 4;
+    const int tid = m.tid, NT = m.NT, N = m.N;
+    const size_t vbuf = ens_reg_vbuf_bytes(m.dim_x, m.dim_y, R);
+    float2 *A = reinterpret_cast<float2 *>(smem_raw);
+    float2 *B = reinterpret_cast<float2 *>(smem_raw + vbuf);
+    uint32_t *C_cur = reinterpret_cast<uint32_t *>(smem_raw + 2 * vbuf);
+    uint32_t *C_oth = C_cur + 3 * (size_t)N;
+#ifdef __CUDACC__
+    uint64_t *bar_v = reinterpret_cast<uint64_t *>(smem_raw + 2 * vbuf + (size_t)24 * N), *bar_c = bar_v + 1;
+    uint32_t phase_v = 0, phase_c = 0;
+    const uint32_t v_bytes = 8u * N, c_bytes = 12u * N;
+#else
+    async = false;
+#endif
+
+    int grid = env.block;
+    if (grid >= a.batch) return;
+    // ---- prologue: the first grid's state ------------------------------------------------------------------
+#ifdef __CUDACC__
+    if (async) {
+        if (tid == 0) {
+            mbar_init(bar_v, 1);
+            mbar_init(bar_c, 1);
+            ens_fence_proxy_async();
+        }
+        env.sync();
+        if (tid == 0) {
+            ens_bulk_load(A, a.v + (size_t)grid * N, v_bytes, bar_v);
+            ens_bulk_load(C_cur, a.c + (size_t)grid * N * 3, c_bytes, bar_c);
+        }
+        mbar_wait(bar_v, phase_v); phase_v ^= 1;
+        mbar_wait(bar_c, phase_c); phase_c ^= 1;
+    } else
+#endif
+    {
+        ens_copy_in(A, a.v + (size_t)grid * N, 2 * N, vec16, true, tid, NT);
+        ens_copy_in(C_cur, a.c + (size_t)grid * N * 3, 3 * N, vec16, false, tid, NT);
+        env.sync();
+    }
+
+    for (; grid < a.batch; grid += env.nblocks) {
+        const int next = grid + env.nblocks;
+        const bool has_next = next < a.batch;
+        for (int step = 0; step < a.n_steps; step++) {
+            const bool last = step == a.n_steps - 1;
+            ens_advect_velocity<R, U>(m, a, A, B);
+            env.sync();
+#ifdef __CUDACC__
+            // the previous grid's dye must have left C_oth before anything is written there (this step's dye advect, or
+            // the bulk load below); thread 0 reaches the barriers of the projection only after this wait
+            if (async && step == 0 && tid == 0) ens_bulk_wait_read<0>();
+#endif
+            if (last && has_next) {         // the next grid's dye -> the dye buffer this step does not use
+#ifdef __CUDACC__
+                if (async) {
+                    if (tid == 0) ens_bulk_load(C_oth, a.c + (size_t)next * N * 3, c_bytes, bar_c);
+                } else
+#endif
+                    ens_copy_in(C_oth, a.c + (size_t)next * N * 3, 3 * N, vec16, false, tid, NT);
+            }
+            ens_drags(m, a, B, step, grid, env);
+            ens_project(m, a, reinterpret_cast<float *>(A), B, env);
+            if (!last) {
+                env.sync();
+                ens_advect_dye<R, U>(m, a, B, SmemFetch<RgbPayload>{C_cur, m.dim_x}, C_oth);
+                env.sync();
+                // pointer swaps of ino:255 and ino:286
+                uint32_t *tc = C_cur; C_cur = C_oth; C_oth = tc;
+                float2 *tv = A; A = B; B = tv;
+                continue;
+            }
+#ifdef __CUDACC__
+            if (async) ens_fence_proxy_async();         // B (and the mailboxes in A) before the bulk copies below
+#endif
+            env.sync();
+            // the projected velocity is final: out it goes; A (advect source, then mailboxes) is dead: in comes the next
+            // grid's velocity — both under the dye advect.  (No pointer swap: the next grid's velocity is in A.)
+#ifdef __CUDACC__
+            if (async) {
                 if (tid == 0) {
-                    const size_t slot = (size_t)step * a.batch + grid;
-                    const int cnt = min(a.counts[slot], a.max_drags);
-                    const fs_drag *dr = a.drags + slot * a.max_drags;
-                    for (int q = 0; q < cnt; q++) {
-                        const fs_drag m = dr[q];
-                        if (m.cy < dim_x && m.cx < dim_y) B[m.cx * dim_x + m.cy] = make_float2(m.vy, m.vx);
-                    }
+                    ens_bulk_store(a.v + (size_t)grid * N, B, v_bytes);
+                    if (has_next) ens_bulk_load(A, a.v + (size_t)next * N, v_bytes, bar_v);
                 }
-                env.sync();
-            }
-            // ---- projection in registers; the mailboxes live in A, which is dead now -----------------------
-            float *mail = reinterpret_cast<float *>(A);
-            float p[R][4], d[R][4];
-            if (tid < MS) mail[o_zero + tid] = 0.0f;       // (first read after the first half-sweep's barrier)
-            if (act) {
-                // divergence (ino:274, finitediff.cpp:9-39) of the block from B and its one-node ring
-                float vx[R][4], vy[R][4], xl[R], xr[R], yd[4], yu[4];
-                if (even_x) {
-                    // dim_x even: every row of the block starts 16-byte aligned, two nodes per load
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            const float4 t = *reinterpret_cast<const float4 *>(B + row[r] + 2 * h);
-                            vx[r][2 * h] = t.x; vy[r][2 * h] = t.y; vx[r][2 * h + 1] = t.z; vy[r][2 * h + 1] = t.w;
-                        }
-                    }
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const float4 td = *reinterpret_cast<const float4 *>(B + row_dn + 2 * h);
-                        const float4 tu = *reinterpret_cast<const float4 *>(B + row_up + 2 * h);
-                        yd[2 * h] = td.y; yd[2 * h + 1] = td.w; yu[2 * h] = tu.y; yu[2 * h + 1] = tu.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-#pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                            const float2 t = B[row[r] + c];
-                            vx[r][c] = t.x;
-                            vy[r][c] = t.y;
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        yd[c] = B[row_dn + c].y;
-                        yu[c] = B[row_up + c].y;
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    xl[r] = B[row[r] + off_l].x;
-                    xr[r] = B[row[r] + 4].x;
-                }
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const int i = i0 + c, j = j0 + r;
-                        const float xm = c > 0 ? vx[r][c > 0 ? c - 1 : 0] : xl[r], xp = c < 3 ? vx[r][c < 3 ? c + 1 : 3] : xr[r];
-                        const float ym = r > 0 ? vy[r > 0 ? r - 1 : 0][c] : yd[c], yp = r < R - 1 ? vy[r < R - 1 ? r + 1 : R - 1][c] : yu[c];
-                        const bool wall = i == 0 || i == dim_x - 1 || j == 0 || j == dim_y - 1;
-                        float sd;
-                        if (!wall) {
-                            sd = __fadd_rn(__fadd_rn(-xm, xp), __fadd_rn(-ym, yp));
-                        } else {
-                            sd = 0.0f;
-                            sd = __fadd_rn(sd, i > 0 ? -xm : vx[r][c]);
-                            sd = __fadd_rn(sd, i < dim_x - 1 ? xp : -vx[r][c]);
-                            sd = __fadd_rn(sd, j > 0 ? -ym : vy[r][c]);
-                            sd = __fadd_rn(sd, j < dim_y - 1 ? yp : -vy[r][c]);
-                        }
-                        // dx*d: the same product every iteration (poisson.cpp:88,109)
-                        const float dd = __fmul_rn(a.k.dx, __fmul_rn(sd, a.two_dx_inv));
-                        d[r][c] = __uint_as_float(__float_as_uint(dd) & cm[c] & rm[r]);
-                        p[r][c] = 0.0f;                    // poisson.cpp:117-119
-                    }
-                }
-            }
-            // ---- red-black SOR (ino:275) ---------------------------------------------------------------------
-            if (a.iters > 0) {
-                if (ragged)
-                    ens_sor<R, true>(p, d, coef, cm, rm, mail + o_mine, mail + o_left, mail + o_right, mail + o_down, mail + o_up, a.k, a.iters, act, env);
-                else
-                    ens_sor<R, false>(p, d, coef, cm, rm, mail + o_mine, mail + o_left, mail + o_right, mail + o_down, mail + o_up, a.k, a.iters, act, env);
-            } else {
-                if (act)
-                    for (int w = 0; w < MS; w++) mail[o_mine + w] = 0.0f;
-                env.sync();
-            }
-            // ---- subtract gradient (ino:276, finitediff.cpp:41-82), in place on B ----------------------------
-            if (act) {
-                float hl[R], hr[R], vd[4], vu[4];
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    hl[r] = mail[o_left + 2 * r + 1];
-                    hr[r] = mail[o_right + 2 * r + 0];
-                }
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    vd[c] = mail[o_down + 2 * R + 4 + c];
-                    vu[c] = mail[o_up + 2 * R + c];
-                }
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    float gx[4], gy[4];                    // (p_right - p_left) / 2dx, (p_up - p_down) / 2dx
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const int i = i0 + c, j = j0 + r;
-                        const float pc = p[r][c];
-                        const float pl = i > 0 ? (c > 0 ? p[r][c > 0 ? c - 1 : 0] : hl[r]) : pc;
-                        const float pr = i < dim_x - 1 ? (c < 3 ? p[r][c < 3 ? c + 1 : 3] : hr[r]) : pc;
-                        const float pd = j > 0 ? (r > 0 ? p[r > 0 ? r - 1 : 0][c] : vd[c]) : pc;
-                        const float pu = j < dim_y - 1 ? (r < R - 1 ? p[r < R - 1 ? r + 1 : R - 1][c] : vu[c]) : pc;
-                        gx[c] = __fmul_rn(__fsub_rn(pr, pl), a.two_dx_inv);
-                        gy[c] = __fmul_rn(__fsub_rn(pu, pd), a.two_dx_inv);
-                    }
-                    if (even_x) {
-                        // dim_x even: nodes are inside the grid in pairs, 16 bytes per access
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            if (cm[2 * h] & rm[r]) {
-                                float4 t = *reinterpret_cast<const float4 *>(B + row[r] + 2 * h);
-                                t.x = __fsub_rn(t.x, gx[2 * h]);
-                                t.y = __fsub_rn(t.y, gy[2 * h]);
-                                t.z = __fsub_rn(t.z, gx[2 * h + 1]);
-                                t.w = __fsub_rn(t.w, gy[2 * h + 1]);
-                                *reinterpret_cast<float4 *>(B + row[r] + 2 * h) = t;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                            if (cm[c] & rm[r]) {
-                                float2 c0 = B[row[r] + c];
-                                c0.x = __fsub_rn(c0.x, gx[c]);
-                                c0.y = __fsub_rn(c0.y, gy[c]);
-                                B[row[r] + c] = c0;
-                            }
-                        }
-                    }
-                }
-            }
-            env.sync();
-            // ---- advect dye, free-slip sampling (ino:282) with the projected velocity: C1 -> C2 ---------------
+            } else
+#endif
             {
-                DyeFetch fetch{C1, dim_x};
-                float fi = adv_i0, fj = adv_j0;
-                for (int nb = tid; nb < N; nb += U * NT) {
-                    uint32_t res[U][3];
-                    float si[U], sj[U];
-                    bool oob[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int n = min(nb + u * NT, N - 1);
-                        const float2 vel = B[n];
-                        si[u] = __fsub_rn(fi, __fmul_rn(vel.x, a.dt));
-                        sj[u] = __fsub_rn(fj, __fmul_rn(vel.y, a.dt));
-                        oob[u] = sample_interior<RgbPayload>(res[u], fetch, si[u], sj[u], gx2, gy2);
-                        fi += adv_di;
-                        fj += adv_dj;
-                        if (fi >= fdim_x) { fi -= fdim_x; fj += 1.0f; }
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int n = nb + u * NT;
-                        if (n < N) {
-                            if (oob[u]) sample<RgbPayload>(res[u], fetch, si[u], sj[u], dim_x, dim_y, false);
-                            C2[3 * n + 0] = res[u][0];
-                            C2[3 * n + 1] = res[u][1];
-                            C2[3 * n + 2] = res[u][2];
-                        }
-                    }
-                }
+                ens_copy_out(a.v + (size_t)grid * N, B, 2 * N, vec16, true, tid, NT);
+                if (has_next) ens_copy_in(A, a.v + (size_t)next * N, 2 * N, vec16, true, tid, NT);
             }
+            ens_advect_dye_in_place<R, U>(m, a, B, C_cur, env);
+#ifdef __CUDACC__
+            if (async) ens_fence_proxy_async();         // C_cur before its bulk store
+#endif
+            env.sync();
+        }
+        // ---- the grid's dye leaves; wait for the next grid's state ------------------------------------------------
+#ifdef __CUDACC__
+        if (async) {
+            if (tid == 0) {
+                ens_bulk_store(a.c + (size_t)grid * N * 3, C_cur, c_bytes);
+                ens_bulk_wait_read<1>();    // the velocity store (the older group) no longer reads B: the next advect may write it
+            }
+            if (has_next) {
+                mbar_wait(bar_v, phase_v); phase_v ^= 1;
+                mbar_wait(bar_c, phase_c); phase_c ^= 1;
+            }
+        } else
+#endif
+            ens_copy_out(a.c + (size_t)grid * N * 3, C_cur, 3 * N, vec16, false, tid, NT);
+        uint32_t *tc = C_cur; C_cur = C_oth; C_oth = tc;
+        env.sync();
+    }
+#ifdef __CUDACC__
+    if (async && tid == 0) ens_bulk_wait_all();     // shared memory must outlive the last bulk stores
+#endif
+}
+
+// PIPE: compile the pipelined flow too (it keeps up to 4R dye results per thread in registers: R = 2 only)
+template <int R, bool PIPE, class Env>
+__device__ __forceinline__ void ens_reg_body_resident(const EnsArgs &a, unsigned char *smem_raw, const Env &env)
+{
+    EnsMap<R> m;
+    ens_map_init(m, a, env.tid, env.nthreads);
+    // 16-byte copies between global and shared memory need N % 4 == 0 (12N and 8N multiples of 16) and aligned arrays
+    const bool vec16 = (m.N & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.v) | reinterpret_cast<uintptr_t>(a.c)) & 15) == 0;
+    if constexpr (PIPE) {
+        // (a call of many steps amortises the state I/O anyway, and the plain flow's steps are a few % faster)
+        const bool async = Env::kAsync && vec16 && a.n_steps <= a.pipe_max_steps;
+        if (async || Env::kEmulatePipe) {
+            ens_resident_pipelined<R>(m, a, smem_raw, vec16, async, env);
+            return;
+        }
+    }
+    ens_resident_sync<R>(m, a, smem_raw, vec16, env);
+}
+
+// Dye STREAMED through L1/L2 (16 B/node of shared memory: grids too large for 40 B/node): the dye advect gathers it
+// from global memory and writes the result back; between the steps of one call it ping-pongs between the caller's
+// array and a per-CTA scratch slot that stays L2-resident.
+template <int R, class Env>
+__device__ __forceinline__ void ens_reg_body_streamed(const EnsArgs &a, unsigned char *smem_raw, const Env &env)
+{
+    constexpr int U = R == 2 ? 2 : 4;
+    EnsMap<R> m;
+    ens_map_init(m, a, env.tid, env.nthreads);
+    const int tid = m.tid, NT = m.NT, N = m.N;
+    const size_t vbuf = ens_reg_vbuf_bytes(m.dim_x, m.dim_y, R);
+    float2 *A = reinterpret_cast<float2 *>(smem_raw);
+    float2 *B = reinterpret_cast<float2 *>(smem_raw + vbuf);
+    const bool vec16 = (N & 1) == 0 && (reinterpret_cast<uintptr_t>(a.v) & 15) == 0;
+    uint32_t *scratch = a.scratch + (size_t)env.block * N * 3;
+
+    for (int grid = env.block; grid < a.batch; grid += env.nblocks) {
+        uint32_t *user_c = a.c + (size_t)grid * N * 3;
+        uint32_t *C1 = user_c, *C2 = scratch;
+        ens_copy_in(A, a.v + (size_t)grid * N, 2 * N, vec16, true, tid, NT);
+        env.sync();
+        for (int step = 0; step < a.n_steps; step++) {
+            if (step == a.n_steps - 1 && grid + env.nblocks < a.batch) {
+                const char *nv = reinterpret_cast<const char *>(a.v + (size_t)(grid + env.nblocks) * N);
+                for (int l = tid * 128; l < N * 8; l += NT * 128) prefetch_l2(nv + l);
+            }
+            ens_advect_velocity<R, U>(m, a, A, B);
+            env.sync();
+            ens_drags(m, a, B, step, grid, env);
+            ens_project(m, a, reinterpret_cast<float *>(A), B, env);
+            env.sync();
+            ens_advect_dye<R, U>(m, a, B, DyeFetch{C1, m.dim_x}, C2);
             env.sync();                     // (CTA-scope ordering of the dye stores before the next step's reads)
             // pointer swaps of ino:255 and ino:286
             uint32_t *tc = C1; C1 = C2; C2 = tc;
             float2 *tv = A; A = B; B = tv;
         }
-
-        // ---- store the grid's state ----------------------------------------------------------------------
-        float2 *ov = a.v + (size_t)grid * N;
-        if (vec16) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(A);
-            uint4 *dst = reinterpret_cast<uint4 *>(ov);
-            for (int n = tid; n < N / 2; n += NT) dst[n] = src[n];
-        } else {
-            for (int n = tid; n < N; n += NT) ov[n] = A[n];
-        }
-        if (C1 != user_c) {                 // the final dye sits in shared memory / in the scratch slot
-            if (DYE_SMEM && vec16) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(C1);
-                uint4 *dst = reinterpret_cast<uint4 *>(user_c);
-                for (int n = tid; n < 3 * N / 4; n += NT) dst[n] = src[n];
-            } else {
-                for (int n = tid; n < 3 * N; n += NT) user_c[n] = C1[n];
-            }
-        }
+        ens_copy_out(a.v + (size_t)grid * N, A, 2 * N, vec16, true, tid, NT);
+        if (C1 != user_c)                   // the final dye sits in the scratch slot
+            for (int n = tid; n < 3 * N; n += NT) user_c[n] = C1[n];
         env.sync();
-        if constexpr (!DYE_SMEM) C2 = a.scratch + (size_t)env.block * N * 3;   // next grid: C1 = its own array again
     }
+}
+
+template <int R, bool DYE_SMEM, class Env, bool PIPE = (R == 2)>
+__device__ __forceinline__ void ens_reg_body(const EnsArgs &a, unsigned char *smem_raw, const Env &env)
+{
+    if constexpr (DYE_SMEM)
+        ens_reg_body_resident<R, PIPE>(a, smem_raw, env);
+    else
+        ens_reg_body_streamed<R>(a, smem_raw, env);
 }
 
 }  // namespace fs

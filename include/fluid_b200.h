@@ -93,7 +93,9 @@ int  fs_ctx_synchronize(fs_ctx *ctx);
  *   "ensemble": kernel behind fs_ensemble_step*: 0 (default) = automatic — the register-tiled projection
  *              (csrc/ensemble_reg.cuh), first-generation kernel for shapes it does not take; 1-4 = first
  *              generation with the dye streamed through L1/L2, 5 = first generation, automatic;
- *              6/7/8/9 = register-tiled with 2/4/6/8 rows per thread; 12/14/16/18 = the same, dye streamed
+ *              6/7/8/9 = register-tiled with 2/4/6/8 rows per thread; 12/14/16/18 = the same, dye streamed;
+ *              20/21 = automatic with the bulk-copy pipelined state I/O forced on / off (default: on for calls
+ *              of up to 6 steps)
  *   "num_sms": (read-only) SMs of the context's device */
 int  fs_ctx_set_option(fs_ctx *ctx, const char *name, int value);
 int  fs_ctx_get_option(fs_ctx *ctx, const char *name, int *value);

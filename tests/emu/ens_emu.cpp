@@ -12,7 +12,10 @@
 
 namespace {
 
+template <bool PIPE>
 struct EnvHost {
+    static constexpr bool kAsync = false;       // no bulk copies on the host:
+    static constexpr bool kEmulatePipe = PIPE;  // ... the pipelined flow makes them cooperatively at the same program points
     int tid, nthreads, block, nblocks;
     pthread_barrier_t *bar;
     void sync() const { pthread_barrier_wait(bar); }
@@ -21,17 +24,28 @@ struct EnvHost {
 struct Job {
     const fs::EnsArgs *a;
     unsigned char *smem;
-    EnvHost env;
-    int R, dye_smem;
+    int tid, nthreads, block, nblocks;
+    pthread_barrier_t *bar;
+    int R, dye_smem, pipe;
 };
+
+template <int R, bool PIPE>
+void run_rp(const Job &j)
+{
+    const EnvHost<PIPE> env{j.tid, j.nthreads, j.block, j.nblocks, j.bar};
+    if (j.dye_smem)
+        fs::ens_reg_body<R, true>(*j.a, j.smem, env);
+    else
+        fs::ens_reg_body<R, false>(*j.a, j.smem, env);
+}
 
 template <int R>
 void run_r(const Job &j)
 {
-    if (j.dye_smem)
-        fs::ens_reg_body<R, true>(*j.a, j.smem, j.env);
+    if (j.pipe)
+        run_rp<R, true>(j);
     else
-        fs::ens_reg_body<R, false>(*j.a, j.smem, j.env);
+        run_rp<R, false>(j);
 }
 
 void *thread_main(void *arg)
@@ -49,10 +63,11 @@ void *thread_main(void *arg)
 }  // namespace
 
 // v: [batch][dim_y][dim_x] float2, c: [batch][dim_y][dim_x][3] uint32 — updated in place like fs_ensemble_step.
-// nblocks "CTAs" walk the batch (run one after the other); threads = 0 picks the launcher's CTA size.
+// nblocks "CTAs" walk the batch (run one after the other); threads = 0 picks the launcher's CTA size; pipe = 1 runs
+// the pipelined flow of the dye-resident R = 2 kernel (ens_resident_pipelined) with cooperative copies.
 extern "C" int ens_emu_step(float *v, uint32_t *c, const fs_drag *drags, const int *counts, int max_drags, int batch,
                             int dim_x, int dim_y, float dt, float dx, int iters, float omega, int n_steps, int R,
-                            int dye_smem, int nblocks, int threads)
+                            int dye_smem, int nblocks, int threads, int pipe)
 {
     if (R < 2 || R > 8 || R % 2 || dim_x < 2 || dim_y < 2 || batch <= 0 || nblocks <= 0) return -1;
     const int n = dim_x * dim_y;
@@ -65,6 +80,7 @@ extern "C" int ens_emu_step(float *v, uint32_t *c, const fs_drag *drags, const i
     a.counts = counts;
     a.max_drags = max_drags; a.batch = batch; a.dim_x = dim_x; a.dim_y = dim_y; a.iters = iters; a.n_steps = n_steps;
     a.dt = dt;
+    a.pipe_max_steps = 0x7fffffff;
     a.two_dx_inv = 1.0f / (2.0f * dx);
     a.k = fs::make_sor_coef(dx, omega);
     if (threads <= 0) {
@@ -85,7 +101,7 @@ extern "C" int ens_emu_step(float *v, uint32_t *c, const fs_drag *drags, const i
         pthread_attr_init(&attr);
         pthread_attr_setstacksize(&attr, 256 * 1024);
         for (int t = 0; t < threads; t++) {
-            jobs[t] = Job{&a, base, EnvHost{t, threads, b, nblocks < batch ? nblocks : batch, &bar}, R, dye_smem};
+            jobs[t] = Job{&a, base, t, threads, b, nblocks < batch ? nblocks : batch, &bar, R, dye_smem, pipe};
             if (pthread_create(&th[t], &attr, thread_main, &jobs[t]) != 0) return -3;
         }
         for (int t = 0; t < threads; t++) pthread_join(th[t], nullptr);

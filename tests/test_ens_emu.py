@@ -29,12 +29,12 @@ def emu():
                         "-I", CUDA_INC, "-o", EMU_SO, src], check=True, cwd=EMU_DIR)
     lib = ctypes.CDLL(EMU_SO)
     vp, I, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
-    lib.ens_emu_step.argtypes = [vp, vp, vp, vp, I, I, I, I, f, f, I, f, I, I, I, I, I]
+    lib.ens_emu_step.argtypes = [vp, vp, vp, vp, I, I, I, I, f, f, I, f, I, I, I, I, I, I]
     lib.ens_emu_step.restype = I
     return lib
 
 
-def run_case(emu, port, shape, iters, batch, n_steps, R, dye_smem, nblocks=2, threads=0, vmax=90.0):
+def run_case(emu, port, shape, iters, batch, n_steps, R, dye_smem, nblocks=2, threads=0, vmax=90.0, pipe=0):
     from esp32_fluid_simulation_b200 import synth
     dim_x, dim_y = shape
     max_drags = 4
@@ -49,7 +49,7 @@ def run_case(emu, port, shape, iters, batch, n_steps, R, dye_smem, nblocks=2, th
             drags[s, b, :k] = synth.drags(dim_x, dim_y, s * 1000 + b, n=max_drags, vmax=300.0)[:k]
     gv, gc = v.copy(), c.copy()
     rc = emu.ens_emu_step(gv.ctypes.data, gc.ctypes.data, drags.ctypes.data, counts.ctypes.data, max_drags, batch,
-                          dim_x, dim_y, synth.DT, 1.0, iters, 1.96, n_steps, R, int(dye_smem), nblocks, threads)
+                          dim_x, dim_y, synth.DT, 1.0, iters, 1.96, n_steps, R, int(dye_smem), nblocks, threads, pipe)
     assert rc == 0
     for b in range(batch):
         ov, oc = v[b].copy(), c[b].copy()
@@ -88,3 +88,16 @@ def test_ens_reg_source_reference_shape(emu, port):
 def test_ens_reg_fast_velocities(emu, port):
     """CFL >> 1: most backtraces leave the grid, so the general sample() redo path carries the step."""
     run_case(emu, port, (13, 11), 3, 2, 2, 4, True, vmax=900.0)
+
+
+@pytest.mark.parametrize("shape,iters,batch,n_steps,nblocks", [
+    ((16, 12), 3, 5, 1, 2),      # one step per call: every step is a grid's last (dye in place, both prefetches in it)
+    ((16, 12), 3, 5, 3, 2),      # ping-pong steps, then the in-place one
+    ((16, 12), 2, 4, 2, 4),      # one grid per CTA: nothing to prefetch
+    ((13, 11), 3, 3, 2, 1),      # ragged, one CTA walks all grids
+    ((80, 60), 2, 2, 1, 1),      # the benchmark shape with the launcher's CTA size
+])
+def test_ens_reg_pipelined_flow_on_cpu_threads(emu, port, shape, iters, batch, n_steps, nblocks):
+    """The dye-resident R = 2 kernel's PIPELINED flow (in-place dye advect in a grid's last step, next grid's
+    state copied in under it) with the bulk copies replaced by cooperative ones at the same program points."""
+    run_case(emu, port, shape, iters, batch, n_steps, 2, True, nblocks=nblocks, pipe=1)

@@ -381,10 +381,11 @@ def test_4096_size_independent_properties(ctx):
 
 @pytest.mark.parametrize("shape,iters,batch,n_steps", [((61, 81), 10, 5, 1), ((80, 60), 10, 300, 3), ((60, 80), 7, 4, 2),
                                                        ((7, 3), 4, 3, 2), ((2, 2), 3, 2, 1), ((64, 90), 10, 2, 1)])
-@pytest.mark.parametrize("variant", [0, 5, 6, 7, 8, 9, 14])
+@pytest.mark.parametrize("variant", [0, 5, 6, 7, 8, 9, 14, 20, 21])
 def test_ensemble_step(ctx, oracle, shape, iters, batch, n_steps, variant):
     """variant = option "ensemble": 0 automatic (register-tiled projection, ensemble_reg.cuh), 5 the
-    first-generation kernel, 6-9 register-tiled with 2/4/6/8 rows per thread, 14 = 4 rows, dye streamed."""
+    first-generation kernel, 6-9 register-tiled with 2/4/6/8 rows per thread, 14 = 4 rows, dye streamed, 20 / 21 =
+    automatic with the bulk-copy pipelined flow forced on / off."""
     from esp32_fluid_simulation_b200 import synth
     dim_x, dim_y = shape
     if variant not in (0, 5) and batch > 8:
