@@ -453,7 +453,9 @@ def bench_single(args, fb, synth, torch):
         extra["ensemble"] = {"workload": f"{eb} independent {ex}x{ey} grids, K={ek}, one CTA per grid, state resident in "
                                          "shared memory (BASELINE.json configs[1])", "results": ens,
                              "kernel": "ensemble_reg_kernel<2,640,1> (csrc/ensemble_reg.cuh): projection in registers, "
-                                       "4x2-node block per thread, rim values through per-thread mailboxes",
+                                       "4x2-node block per thread, rim values through per-thread mailboxes; calls of "
+                                       "<= 6 steps move the state with cp.async.bulk copies under the neighbouring "
+                                       "grids' compute",
                              "bound": "instruction issue 62 % / shared-memory wavefronts 65 % (profiles/"
                                       "r02_ncu_ensemble_reg_r2*.json), not HBM: state I/O is 40 B/node per CALL"}
         del ev, ec
