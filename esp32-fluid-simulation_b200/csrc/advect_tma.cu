@@ -155,8 +155,11 @@ struct TmaAdvectArgs {
 // and the prefetch registers cut the resident CTAs from 3-4 to 2-3 per SM, and this kernel hides its
 // shared-memory and ALU latencies with resident warps, not with a deeper pipeline; one tile per CTA
 // stays.)
+// (launch bounds: the dye's 62 KB of tiles allow 3 CTAs per SM, so its build may use up to 85 registers — 60 instead of
+// 48 measured 1 % faster; squeezing the velocity build into 40 registers for 6 CTAs per SM instead of 5 measured 3 %
+// SLOWER, it keeps the default)
 template <class P, bool STORE_TMA>
-__global__ void __launch_bounds__(AT_THREADS)
+__global__ void __launch_bounds__(AT_THREADS, P::NC == 2 ? 1 : 3)
 advect_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                   const TmaAdvectArgs a)
 {
