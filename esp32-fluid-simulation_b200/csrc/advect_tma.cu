@@ -159,7 +159,7 @@ struct TmaAdvectArgs {
 // 48 measured 1 % faster; squeezing the velocity build into 40 registers for 6 CTAs per SM instead of 5 measured 3 %
 // SLOWER, it keeps the default)
 template <class P, bool STORE_TMA>
-__global__ void __launch_bounds__(AT_THREADS, P::NC == 2 ? 1 : 3)
+__global__ void __launch_bounds__(AT_THREADS, P::NC == 2 ? 5 : 3)
 advect_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                   const TmaAdvectArgs a)
 {
