@@ -85,6 +85,7 @@ struct fs_dist {
     unsigned long long exchanges;
     // SOR plan
     int T, n_pass;
+    int sched[WORK_SLOTS];             // iterations of each SOR pass
     int D, A, vw, cw;                  // div ring, advect halo, exchanged ghost widths of v and dye
     bool v_halo_ok;                    // the current velocity's ghosts are valid to width vw
     float *p_last;
@@ -222,17 +223,35 @@ int fs_dist_create(fs_dist **out, const fs_dist_config *cfg, fs_ctx *ctx)
     d->me = d->ranks[cfg->rank];
     // the SOR plan: T iterations per pass; the LAST pass also computes the gradient's ring
     d->T = ctx->opt_sor_t < 1 ? 1 : ctx->opt_sor_t;
-    d->n_pass = cfg->iters > 0 ? (cfg->iters + d->T - 1) / d->T : 0;
-    int need_d = 0;
-    for (int k = 0; k < d->n_pass; k++) {
-        const int t = cfg->iters - k * d->T < d->T ? cfg->iters - k * d->T : d->T;
-        const int need = 2 * t + (k == d->n_pass - 1 ? 1 : 0);
-        if (need > need_d) need_d = need;
-    }
-    if (cfg->world == 1) need_d = 0;
-    d->D = round_up4(need_d);
     d->A = cfg->world > 1 ? cfg->advect_halo : 0;
-    d->vw = round_up4(d->D + 1 + d->A);
+    // Pass schedule: T iterations per pass.  A remainder of 1 or 2 iterations is folded into the FIRST pass when the
+    // ghosts allow it (that pass starts from p = 0: it needs no pressure ghosts, only the divergence on a wider
+    // ring) — one pass and one hand-shake less per step (K = 50, T = 6: 8 + 7 x 6 instead of 8 x 6 + 2; same rule
+    // as core_poisson_solve, api.cu).
+    for (int fold = 1; fold >= 0; fold--) {
+        int n = cfg->iters > 0 ? (cfg->iters + d->T - 1) / d->T : 0;
+        if (n > WORK_SLOTS) {
+            delete d;
+            return FS_ERR_INVALID_ARG;
+        }
+        for (int k = 0; k < n; k++) d->sched[k] = cfg->iters - k * d->T < d->T ? cfg->iters - k * d->T : d->T;
+        if (fold) {
+            const int r = n > 1 ? d->sched[n - 1] : 0;
+            if (n <= 1 || r > 2 || 2 * (d->T + r) > SOR_BLOCKED_MAX_HALF) continue;
+            d->sched[0] = d->T + r;
+            n--;
+        }
+        d->n_pass = n;
+        int need_d = 0;
+        for (int k = 0; k < n; k++) {
+            const int need = 2 * d->sched[k] + (k == n - 1 ? 1 : 0);
+            if (need > need_d) need_d = need;
+        }
+        if (cfg->world == 1) need_d = 0;
+        d->D = round_up4(need_d);
+        d->vw = round_up4(d->D + 1 + d->A);
+        if (!fold || cfg->world == 1 || d->vw <= ghost) break;   // folded plan does not fit the ghosts: plain plan
+    }
     d->cw = round_up4(d->A + (cfg->frame && cfg->world > 1 ? 1 : 0));   // the frame's far corners lie one node beyond
     // identical verdict on every rank: the widest exchanged strip must fit the ghosts AND the
     // narrowest rectangle of the decomposition (a strip is cut out of the sender's rectangle)
@@ -513,7 +532,7 @@ int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags)
         const unsigned long long base = d->seq;
         for (int k = 0; k < d->n_pass; k++) {
             const bool last = k == d->n_pass - 1;
-            const int t = cfg.iters - k * d->T < d->T ? cfg.iters - k * d->T : d->T;
+            const int t = d->sched[k];
             Geo gp = gw;
             if (last && multi) grow_rect(gw, 1, gp.x0, gp.y0, gp.x1, gp.y1);   // + the gradient's ring
             SorPushArgs push;
@@ -528,7 +547,7 @@ int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags)
                 for (int q = 0; q < d->n_nb; q++) push.wait[q] = flag_slot(d->arena, d->nb[q].dx, d->nb[q].dy);
             }
             if (multi && !last) {                  // the next pass needs this one's rim in the neighbours' ghosts
-                const int t_next = cfg.iters - (k + 1) * d->T < d->T ? cfg.iters - (k + 1) * d->T : d->T;
+                const int t_next = d->sched[k + 1];
                 const int need = 2 * t_next + (k + 1 == d->n_pass - 1 ? 1 : 0);
                 push.n_peers = d->n_nb;
                 push.seq_signal = base + k + 1;

@@ -711,6 +711,8 @@ def bench_decomposed(args, tile_edge: int, iters: int, n_drags: int) -> dict:
     roofline = None
     try:
         plan = [min(sor_t, iters - k) for k in range(0, iters, sor_t)]
+        if len(plan) > 1 and info["sor_passes"] == len(plan) - 1:    # remainder folded into the first pass (dist.cu)
+            plan = [plan[0] + plan[-1]] + plan[1:-1]
 
         def local_solve():
             src, dst = None, f_p
