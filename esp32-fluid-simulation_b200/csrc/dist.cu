@@ -37,7 +37,8 @@
 
 namespace {
 
-constexpr size_t FLAG_BYTES = 256;   // 9 uint64 flag slots, one per direction, padded
+constexpr size_t FLAG_BYTES = 256;   // 3 sets of 9 uint64 flag slots (one per direction): SOR passes + main-stream exchanges,
+                                     // the velocity exchange's side stream, the dye exchange's side stream; padded
 
 struct RankGeo {
     int gx0, gx1, gy0, gy1;   // owned rectangle, global coordinates
@@ -94,6 +95,13 @@ struct fs_dist {
     int cells_x, cells_y;
     cudaEvent_t ev[6];                 // phase boundaries of the LAST step (fs_dist_info: phase_ms)
     bool ev_valid;
+    // the two per-step field exchanges run on side streams, off the critical path (see fs_dist_step):
+    bool c_halo_ok;                    // the current dye's ghosts are valid to width cw
+    cudaStream_t xs_v, xs_c;           // velocity / dye exchange streams (high priority)
+    cudaEvent_t ev_grad, ev_vx, ev_dye, ev_cx;
+    bool vx_pending, cx_pending;       // an exchange is in flight whose completion the main stream has not waited for yet
+    unsigned long long seq_side[3];    // sequence numbers of flag sets 1 and 2 (index 0 unused: set 0 uses `seq`)
+    unsigned int *done_side;           // device: last-block counters of the side-stream exchange kernels [2]
 };
 
 namespace {
@@ -131,9 +139,9 @@ void send_strip(const RankGeo &m, int dx, int dy, int wx, int wy, int &sx0, int 
     sy1 = dy < 0 ? m.y0 + wy : m.y1;
 }
 
-unsigned long long *flag_slot(char *arena_base, int dx, int dy)
+unsigned long long *flag_slot(char *arena_base, int dx, int dy, int set = 0)
 {
-    return reinterpret_cast<unsigned long long *>(arena_base) + ((dy + 1) * 3 + (dx + 1));
+    return reinterpret_cast<unsigned long long *>(arena_base) + set * 9 + ((dy + 1) * 3 + (dx + 1));
 }
 
 unsigned long long timeout_ns(const fs_ctx *ctx)
@@ -142,7 +150,10 @@ unsigned long long timeout_ns(const fs_ctx *ctx)
 }
 
 // one stand-alone exchange kernel for up to 2 fields (velocity: 8 B/node, dye: 12 B/node)
-int exchange_fields(fs_dist *d, const size_t *offs, const int *elem_bytes, const int *widths, int n_fields)
+// set 0: on the context's stream, flag set / sequence shared with the SOR passes; 1 / 2: on the velocity / dye side
+// stream with a flag set, sequence number and last-block counter of its own (their hand-shakes interleave with the
+// SOR passes' in an order that differs from rank to rank)
+int exchange_fields(fs_dist *d, const size_t *offs, const int *elem_bytes, const int *widths, int n_fields, int set = 0)
 {
     if (d->n_nb == 0) return FS_OK;
     fs_ctx *ctx = d->ctx;
@@ -165,15 +176,26 @@ int exchange_fields(fs_dist *d, const size_t *offs, const int *elem_bytes, const
             c.row_words = (sx1 - sx0) * es / 4;
             c.rows = sy1 - sy0;
         }
-        a.signal[k] = flag_slot(n.base, -n.dx, -n.dy);
-        a.wait[k] = flag_slot(d->arena, n.dx, n.dy);
+        a.signal[k] = flag_slot(n.base, -n.dx, -n.dy, set);
+        a.wait[k] = flag_slot(d->arena, n.dx, n.dy, set);
     }
     a.n_copies = nc;
     a.n_peers = d->n_nb;
-    a.seq = ++d->seq;
+    a.seq = set == 0 ? ++d->seq : ++d->seq_side[set];
     a.timeout_ns = timeout_ns(ctx);
     d->exchanges++;
-    return launch_halo_exchange(mk(ctx), a, ctx->halo_done_dev, ctx->status_dev);
+    Launch L = mk(ctx);
+    if (set == 1) L.stream = d->xs_v;
+    if (set == 2) L.stream = d->xs_c;
+    return launch_halo_exchange(L, a, set == 0 ? ctx->halo_done_dev : d->done_side + (set - 1), ctx->status_dev);
+}
+
+// everything the side streams still have in flight (before the fields are overwritten, read back or freed)
+void drain_side_streams(fs_dist *d)
+{
+    if (d->xs_v) cudaStreamSynchronize(d->xs_v);
+    if (d->xs_c) cudaStreamSynchronize(d->xs_c);
+    d->vx_pending = d->cx_pending = false;
 }
 
 }  // namespace
@@ -325,6 +347,29 @@ int fs_dist_create(fs_dist **out, const fs_dist_config *cfg, fs_ctx *ctx)
     }
     for (int k = 0; k < 6; k++) cudaEventCreate(&d->ev[k]);
     d->ev_valid = false;
+    d->xs_v = d->xs_c = nullptr;
+    d->done_side = nullptr;
+    d->vx_pending = d->cx_pending = false;
+    d->c_halo_ok = false;
+    d->seq_side[0] = d->seq_side[1] = d->seq_side[2] = 0;
+    if (d->n_nb > 0) {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // (their few blocks should not queue behind a step's kernels)
+        cudaError_t se = cudaStreamCreateWithPriority(&d->xs_v, cudaStreamNonBlocking, prio_hi);
+        if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&d->xs_c, cudaStreamNonBlocking, prio_hi);
+        if (se == cudaSuccess) se = cudaMalloc(&d->done_side, 2 * sizeof(unsigned int));
+        if (se == cudaSuccess) se = cudaMemset(d->done_side, 0, 2 * sizeof(unsigned int));
+        if (se == cudaSuccess) se = cudaEventCreateWithFlags(&d->ev_grad, cudaEventDisableTiming);
+        if (se == cudaSuccess) se = cudaEventCreateWithFlags(&d->ev_vx, cudaEventDisableTiming);
+        if (se == cudaSuccess) se = cudaEventCreateWithFlags(&d->ev_dye, cudaEventDisableTiming);
+        if (se == cudaSuccess) se = cudaEventCreateWithFlags(&d->ev_cx, cudaEventDisableTiming);
+        if (se != cudaSuccess) {
+            cudaFree(d->arena);
+            cudaFree(d->frame);
+            delete d;
+            return (int)se;
+        }
+    }
     d->cur_v = d->cur_c = 0;
     d->connected = d->n_nb == 0;
     d->seq = 0;
@@ -340,11 +385,18 @@ int fs_dist_destroy(fs_dist *d)
     if (!d) return FS_ERR_INVALID_ARG;
     DeviceGuard guard(d->ctx->device);
     cudaStreamSynchronize(d->ctx->stream);
+    drain_side_streams(d);
     for (int k = 0; k < d->n_nb; k++)
         if (d->nb[k].opened) cudaIpcCloseMemHandle(d->nb[k].base);
     cudaFree(d->arena);
     cudaFree(d->frame);
     for (int k = 0; k < 6; k++) cudaEventDestroy(d->ev[k]);
+    if (d->xs_v) {
+        cudaStreamDestroy(d->xs_v);
+        cudaStreamDestroy(d->xs_c);
+        cudaFree(d->done_side);
+        cudaEventDestroy(d->ev_grad); cudaEventDestroy(d->ev_vx); cudaEventDestroy(d->ev_dye); cudaEventDestroy(d->ev_cx);
+    }
     delete d;
     return FS_OK;
 }
@@ -378,7 +430,9 @@ int fs_dist_info(const fs_dist *d, fs_dist_info_t *info)
     info->div_ring = d->D;
     info->velocity_halo = d->vw;
     info->dye_halo = d->cw;
-    info->exchanges_per_step = d->n_nb ? (d->n_pass > 0 ? d->n_pass : 1) : 0;
+    // hand-shakes per step: one per SOR pass but the last (fused into the passes), the velocity exchange and the dye
+    // exchange (side streams)
+    info->exchanges_per_step = d->n_nb ? (d->n_pass > 0 ? d->n_pass - 1 : 0) + 1 + (d->cw > 0 ? 1 : 0) : 0;
     info->exchanges = d->exchanges;
     info->arena_bytes = d->arena_bytes;
     // phases of the last step (CUDA events on the compute stream): advect+drags+div | SOR passes (with their fused
@@ -436,9 +490,10 @@ int fs_dist_upload(fs_dist *d, const fs_vec2f *v_window, const fs_rgb_uq32 *c_wi
     fs_ctx *ctx = d->ctx;
     DeviceGuard guard(ctx->device);
     const size_t n = (size_t)d->me.nx * d->me.ny;
+    drain_side_streams(d);   // (this rank's pushes of an earlier run; the caller keeps the ranks in step around an upload)
     FS_CUDA_TRY(cudaMemcpyAsync(d->arena + d->off_v[d->cur_v], v_window, n * sizeof(fs_vec2f), cudaMemcpyDefault, ctx->stream));
     FS_CUDA_TRY(cudaMemcpyAsync(d->arena + d->off_c[d->cur_c], c_window, n * sizeof(fs_rgb_uq32), cudaMemcpyDefault, ctx->stream));
-    d->v_halo_ok = false;   // ghosts are refreshed by an exchange before they are read
+    d->v_halo_ok = d->c_halo_ok = false;   // ghosts are refreshed by an exchange before they are read
     return FS_OK;
 }
 
@@ -457,6 +512,7 @@ int fs_dist_download(fs_dist *d, fs_vec2f *v_rect, fs_rgb_uq32 *c_rect, float *p
     if (p_rect) FS_CUDA_TRY(pull(p_rect, (const char *)d->p_last, 4));
     if (div_rect) FS_CUDA_TRY(pull(div_rect, d->arena + d->off_div, 4));
     FS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    drain_side_streams(d);   // after a download on every rank, nobody pushes into anybody's arena any more
     return FS_OK;
 }
 
@@ -486,13 +542,19 @@ int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags)
     fs_rgb_uq32 *c = field<fs_rgb_uq32>(d, d->off_c[d->cur_c]), *c2 = field<fs_rgb_uq32>(d, d->off_c[d->cur_c ^ 1]);
     float *div = field<float>(d, d->off_div);
 
-    // the current velocity's ghosts (fresh state only: afterwards step 4 of the previous step filled them)
-    if (multi && !d->v_halo_ok) {
-        const size_t offs[1] = {d->off_v[d->cur_v]};
-        const int es[1] = {8}, ws[1] = {d->vw};
-        if ((e = exchange_fields(d, offs, es, ws, 1))) return e;
+    // the current velocity's and dye's ghosts (fresh state only: afterwards the previous step's side-stream exchanges
+    // filled them)
+    if (multi && (!d->v_halo_ok || !d->c_halo_ok)) {
+        const size_t offs[2] = {d->off_v[d->cur_v], d->off_c[d->cur_c]};
+        const int es[2] = {8, 12}, ws[2] = {d->vw, d->cw};
+        if ((e = exchange_fields(d, offs, es, ws, d->cw > 0 ? 2 : 1))) return e;
     }
-    d->v_halo_ok = true;
+    d->v_halo_ok = d->c_halo_ok = true;
+    // the velocity ghosts this step's advect gathers from: pushed by the neighbours under the previous step's dye advect
+    if (d->vx_pending) {
+        FS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, d->ev_vx, 0));
+        d->vx_pending = false;
+    }
     cudaEventRecord(d->ev[0], ctx->stream);
 
     // ---- 1. advect v (no-slip) + drags + divergence (ino:253, 264-269, 274) -------------------------
@@ -580,11 +642,29 @@ int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags)
     if ((e = launch_subtract_gradient(mk(ctx), (float2 *)v2, (const float2 *)v_forced, d->p_last, gw, cfg.dx))) return e;
 
     cudaEventRecord(d->ev[3], ctx->stream);
-    // ---- 4. projected velocity + dye halos in ONE exchange kernel --------------------------------------------
+    // ---- 4. halos of the projected velocity and of the dye, OFF the critical path ---------------------------------
+    // The dye advect gathers DYE from the ghosts but (without a frame) starts its backtraces from owned nodes only, and the next step's
+    // velocity advect gathers VELOCITY: so the projected velocity's strips travel on a side stream under this step's
+    // dye advect (the next step waits for them), and the new dye's strips under the NEXT step's advect + SOR (its dye
+    // advect waits for them).  Each side stream has a flag set of its own.  Race freedom as in DESIGN.md 5: a neighbour
+    // reads the ghosts of buffer b only after its own exchange kernel of the same step saw this rank's flag, and read
+    // them last two steps earlier — before the SOR hand-shakes that this rank's push comes after.
     if (multi) {
-        const size_t offs[2] = {d->off_v[d->cur_v ^ 1], d->off_c[d->cur_c]};
-        const int es[2] = {8, 12}, ws[2] = {d->vw, d->cw};
-        if ((e = exchange_fields(d, offs, es, ws, d->cw > 0 ? 2 : 1))) return e;
+        FS_CUDA_TRY(cudaEventRecord(d->ev_grad, ctx->stream));
+        FS_CUDA_TRY(cudaStreamWaitEvent(d->xs_v, d->ev_grad, 0));
+        const size_t offs[1] = {d->off_v[d->cur_v ^ 1]};
+        const int es[1] = {8}, ws[1] = {d->vw};
+        if ((e = exchange_fields(d, offs, es, ws, 1, 1))) return e;
+        FS_CUDA_TRY(cudaEventRecord(d->ev_vx, d->xs_v));
+        d->vx_pending = true;
+        if (d->frame) {                // the frame's far corners are advected from nodes one beyond the rectangle: their
+            FS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, d->ev_vx, 0));   // backtraces start from velocity GHOSTS
+            d->vx_pending = false;
+        }
+        if (d->cx_pending) {           // this step's dye ghosts: pushed under this step's advect + SOR
+            FS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, d->ev_cx, 0));
+            d->cx_pending = false;
+        }
     }
 
     cudaEventRecord(d->ev[4], ctx->stream);
@@ -602,6 +682,15 @@ int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags)
 
     cudaEventRecord(d->ev[5], ctx->stream);
     d->ev_valid = true;
+    if (multi && d->cw > 0) {          // the new dye's strips: under the next step's advect + SOR
+        FS_CUDA_TRY(cudaEventRecord(d->ev_dye, ctx->stream));
+        FS_CUDA_TRY(cudaStreamWaitEvent(d->xs_c, d->ev_dye, 0));
+        const size_t offs[1] = {d->off_c[d->cur_c ^ 1]};
+        const int es[1] = {12}, ws[1] = {d->cw};
+        if ((e = exchange_fields(d, offs, es, ws, 1, 2))) return e;
+        FS_CUDA_TRY(cudaEventRecord(d->ev_cx, d->xs_c));
+        d->cx_pending = true;
+    }
     d->cur_v ^= 1;    // ino:255 / ino:286: the pointer swaps
     d->cur_c ^= 1;
     return FS_OK;
@@ -610,6 +699,10 @@ int fs_dist_step(fs_dist *d, const fs_drag *drags, int n_drags)
 int fs_dist_check(fs_dist *d)
 {
     if (!d) return FS_ERR_INVALID_ARG;
+    {
+        DeviceGuard guard(d->ctx->device);
+        drain_side_streams(d);     // a time-out of a side-stream hand-shake is reported too
+    }
     return fs_tile_check(d->ctx);
 }
 

@@ -487,7 +487,7 @@ class NativeDist:
         i = self._lib.DistInfo()
         self._lib.check(self._L.fs_dist_info(self._h, self._C.byref(i)), "fs_dist_info")
         out = {n: getattr(i, n) for n, _ in i._fields_}
-        out["phase_ms"] = dict(zip(("advect_drags_div", "sor_with_fused_exchanges", "gradient", "velocity_dye_exchange",
+        out["phase_ms"] = dict(zip(("advect_drags_div", "sor_with_fused_exchanges", "gradient", "wait_for_dye_halo",
                                     "dye_advect"), (float(x) for x in i.phase_ms)))
         return out
 

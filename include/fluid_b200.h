@@ -344,7 +344,8 @@ typedef struct fs_dist_info_t {
     unsigned long long exchanges;  /* hand-shakes since creation */
     size_t arena_bytes;
     float phase_ms[5];      /* the LAST step on this rank, CUDA events: advect+drags+divergence | SOR passes incl.
-                               their fused exchanges | gradient | velocity+dye exchange | dye advect (+ frame);
+                               their fused exchanges | gradient | wait for the dye halo (the velocity and dye exchanges run
+                               on side streams under the dye advect / the next step's advect + SOR) | dye advect (+ frame);
                                -1 before the first step.  Querying synchronises with that step. */
 } fs_dist_info_t;
 int fs_dist_create(fs_dist **out, const fs_dist_config *cfg, fs_ctx *ctx);

@@ -4,6 +4,12 @@ import sys
 import numpy as np
 import pytest
 
+# The one-device emulation of a decomposed run (test_gpu_dist.py) keeps up to 8 ranks x 3 streams busy with kernels
+# that wait for each other's flags: with the default 8 hardware work queues, streams share a queue and a waiting
+# kernel can sit in front of the one it waits for.  Must be set before the CUDA context exists.  (A real multi-GPU
+# run has one process and 3 such streams per device and does not need it.)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

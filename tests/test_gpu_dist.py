@@ -150,8 +150,9 @@ def test_native_decomposed_step_matches_oracle(oracle, world, grid, gx, gy, iter
         rem = iters - (passes - 1) * sor_t
         if passes > 1 and rem <= 2 and sor_t + rem <= 8 and info["velocity_halo"] <= ghost and info["sor_passes"] == passes - 1:
             passes -= 1                                          # the remainder was folded into the first pass
-        assert info["exchanges_per_step"] == passes and info["sor_passes"] == passes
-        assert info["exchanges"] == steps * passes + 1          # + the fresh state's velocity halo
+        # hand-shakes: one per SOR pass but the last, + the velocity and the dye exchange on their side streams
+        assert info["exchanges_per_step"] == passes + 1 and info["sor_passes"] == passes
+        assert info["exchanges"] == steps * (passes + 1) + 1    # + the fresh state's velocity + dye halo
 
 
 def test_native_decomposed_overrun_is_reported():

@@ -2,6 +2,7 @@
 """Small run of every kernel family for compute-sanitizer (memcheck / racecheck):
    compute-sanitizer --tool racecheck python tools_sanitize.py"""
 import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # emulated ranks x 3 streams wait for each other (tests/conftest.py)
 import sys
 
 import numpy as np
