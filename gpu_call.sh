@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
 N=$1
-timeout 300 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -3
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/bench_n${N}_side.json 2> gpurun_out/bench_n${N}_side.err; tail -c 300 gpurun_out/bench_n${N}_side.err; python -c "
 import json,sys
 d=json.loads(open('gpurun_out/bench_n${N}_side.json').read().strip().splitlines()[-1])
