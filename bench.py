@@ -20,6 +20,11 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# fs_dist keeps three streams per rank busy with kernels that wait for other ranks' flags (the SOR passes and the two
+# side-stream halo exchanges): each needs a hardware work queue of its own, or a waiting kernel can sit in front of the
+# one it waits for.  The default is 8 queues shared with torch's and NCCL's streams; must be set before CUDA starts.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import subprocess
 import sys
 import threading

@@ -348,6 +348,8 @@ typedef struct fs_dist_info_t {
                                on side streams under the dye advect / the next step's advect + SOR) | dye advect (+ frame);
                                -1 before the first step.  Querying synchronises with that step. */
 } fs_dist_info_t;
+/* (A rank keeps three streams busy with kernels that wait for other ranks' flags: run the process with
+ * CUDA_DEVICE_MAX_CONNECTIONS=32 so that each gets a hardware work queue of its own.) */
 int fs_dist_create(fs_dist **out, const fs_dist_config *cfg, fs_ctx *ctx);
 int fs_dist_destroy(fs_dist *d);
 int fs_dist_window(const fs_dist *d, fs_tile *out);          /* this rank's window (pitch = nx) */
