@@ -455,11 +455,23 @@ def bench_single(args, fb, synth, torch):
             ens[f"n_steps={n_steps}"] = {"ms": t_ms, "gcell_steps_per_s": cells / (t_ms * 1e-3) / 1e9,
                                          "grid_steps_per_s": eb * n_steps / (t_ms * 1e-3),
                                          "state_io_GBps": eb * ex * ey * 40 / (t_ms * 1e-3) / 1e9}
+        # the reference's own node grid (61 x 81 nodes = 60 x 80 cells, ino:37-38): odd N, every copy congruent-shifted
+        ens_ref = {}
+        rb, rx, ry = 16384, 61, 81
+        with torch.cuda.stream(stream):
+            rv = (torch.rand(rb, ry, rx, 2, device="cuda", generator=g) - 0.5) * 120.0
+            rc = torch.randint(0, 2 ** 31 - 1, (rb, ry, rx, 3), device="cuda", dtype=torch.int32, generator=g)
+        for n_steps in (1, 16):
+            t_ms = timed(lambda: ctx.ensemble_step(rv, rc, rb, rx, ry, synth.DT, synth.DX, ek, synth.OMEGA, n_steps), reps=3)
+            ens_ref[f"n_steps={n_steps}"] = {"ms": t_ms, "gcell_steps_per_s": rb * rx * ry * n_steps / (t_ms * 1e-3) / 1e9,
+                                             "grid_steps_per_s": rb * n_steps / (t_ms * 1e-3)}
+        del rv, rc
         extra["ensemble"] = {"workload": f"{eb} independent {ex}x{ey} grids, K={ek}, one CTA per grid, state resident in "
                                          "shared memory (BASELINE.json configs[1])", "results": ens,
+                             "reference_node_grid_61x81_x16384": ens_ref,
                              "kernel": "ensemble_reg_kernel<2,640,1> (csrc/ensemble_reg.cuh): projection in registers, "
                                        "4x2-node block per thread, rim values through per-thread mailboxes; calls of "
-                                       "<= 6 steps move the state with cp.async.bulk copies under the neighbouring "
+                                       "<= 3 steps move the state with cp.async.bulk copies under the neighbouring "
                                        "grids' compute",
                              "bound": "instruction issue 62 % / shared-memory wavefronts 65 % (profiles/"
                                       "r02_ncu_ensemble_reg_r2*.json), not HBM: state I/O is 40 B/node per CALL"}

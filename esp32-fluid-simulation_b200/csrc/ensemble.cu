@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(MAXT, 1) ensemble_reg_kernel(const EnsArgs a)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const EnsEnvDevice env{(int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x};
     // the pipelined flow keeps 8 dye results per thread in registers: only the 96-register build of R = 2 has room
-    ens_reg_body<R, DYE_SMEM, EnsEnvDevice, (R == 2 && MAXT <= 640)>(a, smem_raw, env);
+    ens_reg_body<R, DYE_SMEM, EnsEnvDevice, (R == 2)>(a, smem_raw, env);
 }
 
 size_t ensemble_scratch_bytes(int dim_x, int dim_y, int grid) { return (size_t)grid * dim_x * dim_y * 12; }
@@ -296,7 +296,7 @@ bool ensemble_supported(int dim_x, int dim_y, size_t max_smem_optin)
 // to the first generation for shapes it does not take); 1-4 = first generation with streamed dye (see above),
 // 5 = first generation, automatic; 6/7/8/9 = register-tiled with R = 2/4/6/8 rows per thread; 12/14/16/18 =
 // the same with the dye streamed through L1/L2 instead of held in shared memory; 20 / 21 = automatic with the
-// pipelined flow of the dye-resident R = 2 kernel forced on / off (default: on for calls of up to 6 steps).
+// pipelined flow of the dye-resident R = 2 kernel forced on / off (default: on for calls of up to 3 steps).
 struct EnsPlan {
     bool reg;          // register-tiled kernel
     int R;             // rows per thread
@@ -306,7 +306,7 @@ struct EnsPlan {
     int old_variant;   // first generation: its variant number
 };
 constexpr int ENS_REG_DEFAULT_R = 2;
-constexpr int ENS_PIPE_MAX_STEPS = 6;    // measured crossover (80x60, K=10: 5.79 n + 0.30 ms against 5.55 n + 1.88 ms per call of n steps)
+constexpr int ENS_PIPE_MAX_STEPS = 3;    // measured crossover (80x60, K=10: 5.85 n + 0.47 ms pipelined against 5.41 n + 2.07 ms per call of n steps; 61x81: 3)
 constexpr size_t ENS_SMEM_LIMIT = 227 * 1024;
 
 // R = 2 is compiled twice: up to 20 warps (5 per SM sub-partition: 96 registers) and up to 21 (6 on one

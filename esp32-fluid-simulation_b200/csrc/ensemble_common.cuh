@@ -14,8 +14,16 @@ struct SmemFetch {
     __device__ __forceinline__ void operator()(int gi, int gj, typename P::raw_t (&o)[P::NC]) const
     {
         const typename P::raw_t *q = base + (gj * dim_x + gi) * P::NC;
+        if constexpr (P::NC == 2) {
+            // one 8-byte load, stated explicitly: with a run-time offset in `base` the compiler can no longer prove the
+            // alignment and splits it into two 4-byte loads (ncu: the velocity advect's LDS count doubled)
+            const float2 t = *reinterpret_cast<const float2 *>(q);
+            o[0] = t.x;
+            o[1] = t.y;
+        } else {
 #pragma unroll
-        for (int ch = 0; ch < P::NC; ch++) o[ch] = q[ch];
+            for (int ch = 0; ch < P::NC; ch++) o[ch] = q[ch];
+        }
     }
 };
 

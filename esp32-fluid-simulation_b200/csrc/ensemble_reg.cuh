@@ -44,18 +44,24 @@ struct EnsRegLayout {
 
 // threads that own a block of the grid
 __host__ __device__ static inline int ens_reg_blocks(int dim_x, int dim_y, int R) { return ((dim_x + 3) / 4) * ((dim_y + R - 1) / R); }
-// one velocity buffer: N nodes + 4 of padding (a block's clamped loads may run 3 nodes past the end), or
-// the mailboxes of all block threads + the block of zeros, whichever is larger
+// one velocity buffer: N nodes + 6 of padding (a block's clamped loads may run 3 nodes past the end, and the data
+// may start 8 bytes into the buffer, see ens_reg_body_resident), or the mailboxes of all block threads + the block
+// of zeros (+ the same shift), whichever is larger
 __host__ __device__ static inline size_t ens_reg_vbuf_bytes(int dim_x, int dim_y, int R)
 {
-    const size_t v = 8 * ((size_t)dim_x * dim_y + 4);
-    const size_t m = 4 * (size_t)((2 * R + 8) | 1) * ((size_t)ens_reg_blocks(dim_x, dim_y, R) + 1);
-    return ((v > m ? v : m) + 15) & ~(size_t)15;
+    const size_t v = 8 * ((size_t)dim_x * dim_y + 6);
+    const size_t m = 4 * (size_t)((2 * R + 8) | 1) * ((size_t)ens_reg_blocks(dim_x, dim_y, R) + 1) + 16;
+    return ((v > m ? v : m) + 127) & ~(size_t)127;      // (buffers start on 128-byte lines: bulk copies measured 7 % slower
+}                                                       //  end to end from a buffer that was only 16-byte aligned)
+// one dye buffer: 12N bytes + up to 12 bytes of shift + the 16-byte granule a load may over-read
+__host__ __device__ static inline size_t ens_reg_cbuf_bytes(int dim_x, int dim_y)
+{
+    return ((size_t)12 * dim_x * dim_y + 32 + 127) & ~(size_t)127;
 }
 __host__ __device__ static inline size_t ens_reg_smem_bytes(int dim_x, int dim_y, int R, bool dye_smem)
 {
     // dye resident: two dye buffers and two mbarriers (the bulk-copy pipeline of ens_reg_body_resident)
-    return 2 * ens_reg_vbuf_bytes(dim_x, dim_y, R) + (dye_smem ? (size_t)24 * dim_x * dim_y + 16 : 0);
+    return 2 * ens_reg_vbuf_bytes(dim_x, dim_y, R) + (dye_smem ? 2 * ens_reg_cbuf_bytes(dim_x, dim_y) + 16 : 0);
 }
 
 // Interior case of sample<T> (advect.h:38-42) on a cell clamped into the grid: no branches, so the loads of
@@ -272,8 +278,9 @@ __device__ __forceinline__ void ens_drags(const EnsMap<R> &m, const EnsArgs &a, 
 
 // ---- projection in registers (ino:274-276): divergence of B, red-black SOR, gradient subtracted from B in place.
 // `mail` = the velocity buffer that is dead now.  Ends BEFORE the barrier that publishes B.
+// rows16: dim_x is even AND B itself is 16-byte aligned, so every row of a block starts on a 16-byte boundary.
 template <int R, class Env>
-__device__ __forceinline__ void ens_project(const EnsMap<R> &m, const EnsArgs &a, float *mail, float2 *B, const Env &env)
+__device__ __forceinline__ void ens_project(const EnsMap<R> &m, const EnsArgs &a, float *mail, float2 *B, bool rows16, const Env &env)
 {
     constexpr int MS = EnsRegLayout<R>::MAIL_STRIDE;
     const int dim_x = m.dim_x, dim_y = m.dim_y, i0 = m.i0, j0 = m.j0;
@@ -282,8 +289,8 @@ __device__ __forceinline__ void ens_project(const EnsMap<R> &m, const EnsArgs &a
     if (m.act) {
         // divergence (ino:274, finitediff.cpp:9-39) of the block from B and its one-node ring
         float vx[R][4], vy[R][4], xl[R], xr[R], yd[4], yu[4];
-        if (m.even_x) {
-            // dim_x even: every row of the block starts 16-byte aligned, two nodes per load
+        if (rows16) {
+            // every row of the block starts 16-byte aligned, two nodes per load
 #pragma unroll
             for (int r = 0; r < R; r++) {
 #pragma unroll
@@ -382,7 +389,7 @@ __device__ __forceinline__ void ens_project(const EnsMap<R> &m, const EnsArgs &a
                 gx[c] = __fmul_rn(__fsub_rn(pr, pl), a.two_dx_inv);
                 gy[c] = __fmul_rn(__fsub_rn(pu, pd), a.two_dx_inv);
             }
-            if (m.even_x) {
+            if (rows16) {
                 // dim_x even: nodes are inside the grid in pairs, 16 bytes per access
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
@@ -527,6 +534,79 @@ __device__ __forceinline__ void ens_copy_out(void *dst_gmem, const void *src_sme
         ens_copy_batched<uint32_t, 8>(reinterpret_cast<uint32_t *>(dst_gmem), reinterpret_cast<const uint32_t *>(src_smem), words, tid, NT, false);
 }
 
+// CONGRUENT copies: source and destination have the same address modulo 16, so the part of the data that lies between
+// 16-byte boundaries moves in 16-byte pieces whatever N is (for odd N a grid's arrays start 4, 8 or 12 bytes off such a
+// boundary; the kernel shifts its shared-memory data pointers by the same amount).
+// Loads take the whole 16-byte granules the data touches (the few foreign bytes land in the buffers' slack) — except a
+// last granule that would reach beyond the end of the caller's ARRAY, which is copied by words.
+struct EnsCongLoad {
+    const unsigned char *s0;   // first granule
+    unsigned char *d0;
+    uint32_t vec_bytes;        // granules copied whole
+    uint32_t tail_words;       // words after them (last grid of the array only)
+};
+__device__ __forceinline__ EnsCongLoad ens_cong_load_plan(void *dst_data, const void *src, uint32_t bytes, const void *arr_end)
+{
+    const unsigned char *sp = reinterpret_cast<const unsigned char *>(src);
+    if (((reinterpret_cast<uintptr_t>(sp) | bytes) & 15) == 0) {     // everything on 16-byte boundaries (N % 4 == 0): no head,
+        EnsCongLoad q;                                               // no foreign bytes — the short way (one thread makes
+        q.s0 = sp;                                                   // these plans between two barriers of the whole CTA)
+        q.d0 = reinterpret_cast<unsigned char *>(dst_data);
+        q.vec_bytes = bytes;
+        q.tail_words = 0;
+        return q;
+    }
+    const uint32_t h = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 15);
+    const unsigned char *end = sp + bytes;
+    const uint32_t over = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(end) & 15)) & 15);
+    const bool whole = end + over <= reinterpret_cast<const unsigned char *>(arr_end);
+    EnsCongLoad p;
+    p.s0 = sp - h;
+    p.d0 = reinterpret_cast<unsigned char *>(dst_data) - h;
+    const unsigned char *vend = whole ? end + over : end - (reinterpret_cast<uintptr_t>(end) & 15);
+    p.vec_bytes = (uint32_t)(vend - p.s0);
+    p.tail_words = whole ? 0u : (uint32_t)(end - vend) / 4;
+    return p;
+}
+__device__ __forceinline__ void ens_copy_cong_in(void *dst_data, const void *src, uint32_t bytes, const void *arr_end, int tid, int NT)
+{
+    const EnsCongLoad p = ens_cong_load_plan(dst_data, src, bytes, arr_end);
+    ens_copy_batched<uint4, 4>(reinterpret_cast<uint4 *>(p.d0), reinterpret_cast<const uint4 *>(p.s0), (int)(p.vec_bytes / 16), tid, NT, true);
+    if (tid < (int)p.tail_words)
+        reinterpret_cast<uint32_t *>(p.d0 + p.vec_bytes)[tid] = __ldg(reinterpret_cast<const uint32_t *>(p.s0 + p.vec_bytes) + tid);
+}
+// Stores must not touch foreign bytes: words up to the first boundary, 16-byte pieces, words after the last boundary.
+struct EnsCongStore {
+    uint32_t head_words, body_bytes, tail_words;
+};
+__device__ __forceinline__ EnsCongStore ens_cong_store_plan(const void *dst, uint32_t bytes)
+{
+    EnsCongStore p;
+    if (((reinterpret_cast<uintptr_t>(dst) | bytes) & 15) == 0) {
+        p.head_words = 0;
+        p.body_bytes = bytes;
+        p.tail_words = 0;
+        return p;
+    }
+    uint32_t h = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
+    if (h > bytes) h = bytes;
+    p.head_words = h / 4;
+    p.body_bytes = (bytes - h) & ~15u;
+    p.tail_words = (bytes - h - p.body_bytes) / 4;
+    return p;
+}
+__device__ __forceinline__ void ens_copy_cong_out(void *dst, const void *src_data, uint32_t bytes, int tid, int NT)
+{
+    const EnsCongStore p = ens_cong_store_plan(dst, bytes);
+    unsigned char *dp = reinterpret_cast<unsigned char *>(dst);
+    const unsigned char *sp = reinterpret_cast<const unsigned char *>(src_data);
+    const uint32_t h = p.head_words * 4;
+    if (tid < (int)p.head_words) reinterpret_cast<uint32_t *>(dp)[tid] = reinterpret_cast<const uint32_t *>(sp)[tid];
+    ens_copy_batched<uint4, 4>(reinterpret_cast<uint4 *>(dp + h), reinterpret_cast<const uint4 *>(sp + h), (int)(p.body_bytes / 16), tid, NT, false);
+    if (tid < (int)p.tail_words)
+        reinterpret_cast<uint32_t *>(dp + h + p.body_bytes)[tid] = reinterpret_cast<const uint32_t *>(sp + h + p.body_bytes)[tid];
+}
+
 #ifdef __CUDACC__
 // 1-D bulk copies (TMA) and their completion mechanisms
 __device__ __forceinline__ void ens_bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
@@ -548,28 +628,64 @@ __device__ __forceinline__ void ens_bulk_wait_read()
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
 }
 __device__ __forceinline__ void ens_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// the congruent copies as bulk copies, issued by ONE thread from plans it made earlier (off the critical path)
+__device__ __forceinline__ void ens_bulk_load_cong(const EnsCongLoad &p, uint64_t *bar)
+{
+    ens_bulk_load(p.d0, p.s0, p.vec_bytes, bar);
+    for (uint32_t w = 0; w < p.tail_words; w++)          // (the last grid of the caller's array only)
+        reinterpret_cast<uint32_t *>(p.d0 + p.vec_bytes)[w] = __ldg(reinterpret_cast<const uint32_t *>(p.s0 + p.vec_bytes) + w);
+}
+__device__ __forceinline__ void ens_bulk_store_cong(const EnsCongStore &p, void *dst, const void *src_data)
+{
+    unsigned char *dp = reinterpret_cast<unsigned char *>(dst);
+    const unsigned char *sp = reinterpret_cast<const unsigned char *>(src_data);
+    const uint32_t h = p.head_words * 4;
+    if (p.body_bytes)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dp + h), "r"(smem_u32(sp + h)), "r"(p.body_bytes)
+                     : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // (always one group per store: the wait_group counts rely on it)
+    for (uint32_t w = 0; w < p.head_words; w++) reinterpret_cast<uint32_t *>(dp)[w] = reinterpret_cast<const uint32_t *>(sp)[w];
+    for (uint32_t w = 0; w < p.tail_words; w++)
+        reinterpret_cast<uint32_t *>(dp + h + p.body_bytes)[w] = reinterpret_cast<const uint32_t *>(sp + h + p.body_bytes)[w];
+}
 __device__ __forceinline__ void ens_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
 // Env: { int tid, nthreads, block, nblocks; void sync() const; static constexpr bool kAsync, kEmulatePipe; }
 //
-// Dye RESIDENT in shared memory (40 B/node: velocity x2, dye x2), state I/O at the grid boundaries: load, step
-// n_steps times (dye ping-pong between the two buffers, ino:286), store.  The next grid's state is pulled into L2
-// during the last step so that its load pays the L2 latency instead of HBM's.
+// Dye RESIDENT in shared memory (40 B/node: velocity x2, dye x2).  `cong`: the caller's arrays are 16-byte aligned, so
+// every copy between global and shared memory is CONGRUENT (see above): the data pointers of a grid sit `hv` / `hc`
+// bytes into their buffers, hv / hc = the grid's velocity / dye address modulo 16 (0 unless N is odd / not a
+// multiple of 4).  Otherwise plain 8- and 4-byte copies.
+struct EnsResident {
+    unsigned char *va, *vb;        // velocity buffers: advect source (then mailboxes), advect destination / projection
+    unsigned char *ca, *cb;        // dye buffers: current, other
+    const unsigned char *v_end, *c_end;   // ends of the caller's arrays
+    bool cong;
+};
+
+// State I/O at the grid boundaries: load, step n_steps times (dye ping-pong between the two buffers, ino:286), store.
+// The next grid's state is pulled into L2 during the last step so that its load pays the L2 latency instead of HBM's.
 template <int R, class Env>
-__device__ __forceinline__ void ens_resident_sync(const EnsMap<R> &m, const EnsArgs &a, unsigned char *smem_raw, bool vec16,
-                                                  const Env &env)
+__device__ __forceinline__ void ens_resident_sync(const EnsMap<R> &m, const EnsArgs &a, EnsResident rs, const Env &env)
 {
     constexpr int U = R == 2 ? 2 : 4;                      // nodes per thread in flight in the advects
     const int tid = m.tid, NT = m.NT, N = m.N;
-    const size_t vbuf = ens_reg_vbuf_bytes(m.dim_x, m.dim_y, R);
-    float2 *A = reinterpret_cast<float2 *>(smem_raw);
-    float2 *B = reinterpret_cast<float2 *>(smem_raw + vbuf);
-    uint32_t *C1 = reinterpret_cast<uint32_t *>(smem_raw + 2 * vbuf);
-    uint32_t *C2 = C1 + 3 * (size_t)N;
     for (int grid = env.block; grid < a.batch; grid += env.nblocks) {
-        ens_copy_in(A, a.v + (size_t)grid * N, 2 * N, vec16, true, tid, NT);
-        ens_copy_in(C1, a.c + (size_t)grid * N * 3, 3 * N, vec16, false, tid, NT);
+        float2 *gv = a.v + (size_t)grid * N;
+        uint32_t *gc = a.c + (size_t)grid * N * 3;
+        const uint32_t hv = rs.cong ? (uint32_t)(reinterpret_cast<uintptr_t>(gv) & 15) : 0;
+        const uint32_t hc = rs.cong ? (uint32_t)(reinterpret_cast<uintptr_t>(gc) & 15) : 0;
+        float2 *A = reinterpret_cast<float2 *>(rs.va + hv), *B = reinterpret_cast<float2 *>(rs.vb + hv);
+        uint32_t *C1 = reinterpret_cast<uint32_t *>(rs.ca + hc), *C2 = reinterpret_cast<uint32_t *>(rs.cb + hc);
+        const bool rows16 = m.even_x && hv == 0;
+        if (rs.cong) {
+            ens_copy_cong_in(A, gv, 8u * N, rs.v_end, tid, NT);
+            ens_copy_cong_in(C1, gc, 12u * N, rs.c_end, tid, NT);
+        } else {
+            ens_copy_in(A, gv, 2 * N, false, true, tid, NT);
+            ens_copy_in(C1, gc, 3 * N, false, false, tid, NT);
+        }
         env.sync();
         for (int step = 0; step < a.n_steps; step++) {
             if (step == a.n_steps - 1 && grid + env.nblocks < a.batch) {
@@ -581,7 +697,7 @@ __device__ __forceinline__ void ens_resident_sync(const EnsMap<R> &m, const EnsA
             ens_advect_velocity<R, U>(m, a, A, B);
             env.sync();
             ens_drags(m, a, B, step, grid, env);
-            ens_project(m, a, reinterpret_cast<float *>(A), B, env);
+            ens_project(m, a, reinterpret_cast<float *>(A), B, rows16, env);
             env.sync();
             ens_advect_dye<R, U>(m, a, B, SmemFetch<RgbPayload>{C1, m.dim_x}, C2);
             env.sync();
@@ -589,111 +705,127 @@ __device__ __forceinline__ void ens_resident_sync(const EnsMap<R> &m, const EnsA
             uint32_t *tc = C1; C1 = C2; C2 = tc;
             float2 *tv = A; A = B; B = tv;
         }
-        ens_copy_out(a.v + (size_t)grid * N, A, 2 * N, vec16, true, tid, NT);
-        ens_copy_out(a.c + (size_t)grid * N * 3, C1, 3 * N, vec16, false, tid, NT);
+        if (rs.cong) {
+            ens_copy_cong_out(gv, A, 8u * N, tid, NT);
+            ens_copy_cong_out(gc, C1, 12u * N, tid, NT);
+        } else {
+            ens_copy_out(gv, A, 2 * N, false, true, tid, NT);
+            ens_copy_out(gc, C1, 3 * N, false, false, tid, NT);
+        }
         env.sync();
     }
 }
 
-// The same with the state I/O OFF the critical path.  In a grid's LAST step the dye is advected in place, so the other
-// dye buffer is free from the start of that step: it receives the next grid's dye.  The next grid's velocity lands in
-// the dead velocity buffer during that step's dye advect, while this grid's projected velocity is already on its way
-// out; this grid's dye leaves while the next grid's first advect runs.  On the device (`async`: arrays 16-byte
-// aligned, N % 4 == 0) the copies are 1-D bulk copies (cp.async.bulk, SASS UBLKCP) issued by thread 0 and tracked by two
-// mbarriers / bulk groups; in the host emulation (Env::kEmulatePipe) the same copies are made cooperatively at the
-// same program points.
+// The same with the state I/O OFF the critical path (needs `cong`).  In a grid's LAST step the dye is advected in place,
+// so the other dye buffer is free from the start of that step: it receives the next grid's dye.  The next grid's velocity
+// lands in the dead velocity buffer during that step's dye advect, while this grid's projected velocity is already on its
+// way out; this grid's dye leaves while the next grid's first advect runs.  On the device (`async`) the copies are 1-D
+// bulk copies (cp.async.bulk, SASS UBLKCP) issued by thread 0 and tracked by two mbarriers / bulk groups; in the host
+// emulation (Env::kEmulatePipe) the same copies are made cooperatively at the same program points.
 template <int R, class Env>
-__device__ __forceinline__ void ens_resident_pipelined(const EnsMap<R> &m, const EnsArgs &a, unsigned char *smem_raw, bool vec16,
+__device__ __forceinline__ void ens_resident_pipelined(const EnsMap<R> &m, const EnsArgs &a, EnsResident rs, unsigned char *bars,
                                                        bool async, const Env &env)
 {
     constexpr int U = R == 2 ? 2 : 4;
     const int tid = m.tid, NT = m.NT, N = m.N;
-    const size_t vbuf = ens_reg_vbuf_bytes(m.dim_x, m.dim_y, R);
-    float2 *A = reinterpret_cast<float2 *>(smem_raw);
-    float2 *B = reinterpret_cast<float2 *>(smem_raw + vbuf);
-    uint32_t *C_cur = reinterpret_cast<uint32_t *>(smem_raw + 2 * vbuf);
-    uint32_t *C_oth = C_cur + 3 * (size_t)N;
-#ifdef __CUDACC__
-    uint64_t *bar_v = reinterpret_cast<uint64_t *>(smem_raw + 2 * vbuf + (size_t)24 * N), *bar_c = bar_v + 1;
-    uint32_t phase_v = 0, phase_c = 0;
     const uint32_t v_bytes = 8u * N, c_bytes = 12u * N;
+#ifdef __CUDACC__
+    uint64_t *bar_v = reinterpret_cast<uint64_t *>(bars), *bar_c = bar_v + 1;
+    uint32_t phase_v = 0, phase_c = 0;
 #else
     async = false;
+    (void)bars;
 #endif
+    auto head = [](const void *p) { return (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15); };
+    // (Tried: issuing from a lane that owns no block and idles through the projection, with the copies' plans made there
+    // and parked in shared memory — the extra live state pushed the kernel from 64 to 330 bytes of spills: 6.3 -> 7.7 ms.)
 
     int grid = env.block;
     if (grid >= a.batch) return;
     // ---- prologue: the first grid's state ------------------------------------------------------------------
-#ifdef __CUDACC__
-    if (async) {
-        if (tid == 0) {
-            mbar_init(bar_v, 1);
-            mbar_init(bar_c, 1);
-            ens_fence_proxy_async();
-        }
-        env.sync();
-        if (tid == 0) {
-            ens_bulk_load(A, a.v + (size_t)grid * N, v_bytes, bar_v);
-            ens_bulk_load(C_cur, a.c + (size_t)grid * N * 3, c_bytes, bar_c);
-        }
-        mbar_wait(bar_v, phase_v); phase_v ^= 1;
-        mbar_wait(bar_c, phase_c); phase_c ^= 1;
-    } else
-#endif
     {
-        ens_copy_in(A, a.v + (size_t)grid * N, 2 * N, vec16, true, tid, NT);
-        ens_copy_in(C_cur, a.c + (size_t)grid * N * 3, 3 * N, vec16, false, tid, NT);
+        const float2 *gv = a.v + (size_t)grid * N;
+        const uint32_t *gc = a.c + (size_t)grid * N * 3;
+#ifdef __CUDACC__
+        if (async) {
+            if (tid == 0) {
+                mbar_init(bar_v, 1);
+                mbar_init(bar_c, 1);
+                ens_fence_proxy_async();
+            }
+            env.sync();
+            if (tid == 0) {
+                ens_bulk_load_cong(ens_cong_load_plan(rs.va + head(gv), gv, v_bytes, rs.v_end), bar_v);
+                ens_bulk_load_cong(ens_cong_load_plan(rs.ca + head(gc), gc, c_bytes, rs.c_end), bar_c);
+            }
+            mbar_wait(bar_v, phase_v); phase_v ^= 1;
+            mbar_wait(bar_c, phase_c); phase_c ^= 1;
+        } else
+#endif
+        {
+            ens_copy_cong_in(rs.va + head(gv), gv, v_bytes, rs.v_end, tid, NT);
+            ens_copy_cong_in(rs.ca + head(gc), gc, c_bytes, rs.c_end, tid, NT);
+        }
         env.sync();
     }
 
     for (; grid < a.batch; grid += env.nblocks) {
         const int next = grid + env.nblocks;
         const bool has_next = next < a.batch;
+        float2 *gv = a.v + (size_t)grid * N, *gv_next = a.v + (size_t)next * N;
+        uint32_t *gc = a.c + (size_t)grid * N * 3, *gc_next = a.c + (size_t)next * N * 3;
+        const uint32_t hv = head(gv), hc = head(gc);
+        float2 *A = reinterpret_cast<float2 *>(rs.va + hv), *B = reinterpret_cast<float2 *>(rs.vb + hv);
+        uint32_t *C_cur = reinterpret_cast<uint32_t *>(rs.ca + hc), *C_oth = reinterpret_cast<uint32_t *>(rs.cb + hc);
+        const bool rows16 = m.even_x && hv == 0;
         for (int step = 0; step < a.n_steps; step++) {
             const bool last = step == a.n_steps - 1;
             ens_advect_velocity<R, U>(m, a, A, B);
             env.sync();
 #ifdef __CUDACC__
-            // the previous grid's dye must have left C_oth before anything is written there (this step's dye advect, or
-            // the bulk load below); thread 0 reaches the barriers of the projection only after this wait
+            // the previous grid's dye must have left the other dye buffer before anything is written there (this step's
+            // dye advect, or the bulk load below); thread 0 reaches the barriers of the projection only after this wait
             if (async && step == 0 && tid == 0) ens_bulk_wait_read<0>();
 #endif
             if (last && has_next) {         // the next grid's dye -> the dye buffer this step does not use
 #ifdef __CUDACC__
                 if (async) {
-                    if (tid == 0) ens_bulk_load(C_oth, a.c + (size_t)next * N * 3, c_bytes, bar_c);
+                    if (tid == 0) ens_bulk_load_cong(ens_cong_load_plan(rs.cb + head(gc_next), gc_next, c_bytes, rs.c_end), bar_c);
                 } else
 #endif
-                    ens_copy_in(C_oth, a.c + (size_t)next * N * 3, 3 * N, vec16, false, tid, NT);
+                    ens_copy_cong_in(rs.cb + head(gc_next), gc_next, c_bytes, rs.c_end, tid, NT);
             }
+
             ens_drags(m, a, B, step, grid, env);
-            ens_project(m, a, reinterpret_cast<float *>(A), B, env);
+            ens_project(m, a, reinterpret_cast<float *>(A), B, rows16, env);
             if (!last) {
                 env.sync();
                 ens_advect_dye<R, U>(m, a, B, SmemFetch<RgbPayload>{C_cur, m.dim_x}, C_oth);
                 env.sync();
-                // pointer swaps of ino:255 and ino:286
+                // pointer swaps of ino:255 and ino:286 (buffers and data pointers alike)
                 uint32_t *tc = C_cur; C_cur = C_oth; C_oth = tc;
                 float2 *tv = A; A = B; B = tv;
+                unsigned char *tb = rs.ca; rs.ca = rs.cb; rs.cb = tb;
+                tb = rs.va; rs.va = rs.vb; rs.vb = tb;
                 continue;
             }
 #ifdef __CUDACC__
             if (async) ens_fence_proxy_async();         // B (and the mailboxes in A) before the bulk copies below
 #endif
             env.sync();
-            // the projected velocity is final: out it goes; A (advect source, then mailboxes) is dead: in comes the next
-            // grid's velocity — both under the dye advect.  (No pointer swap: the next grid's velocity is in A.)
+            // the projected velocity is final: out it goes; A's buffer (advect source, then mailboxes) is dead: in comes the
+            // next grid's velocity — both under the dye advect.  (No buffer swap: the next grid's velocity is in `va`.)
 #ifdef __CUDACC__
             if (async) {
                 if (tid == 0) {
-                    ens_bulk_store(a.v + (size_t)grid * N, B, v_bytes);
-                    if (has_next) ens_bulk_load(A, a.v + (size_t)next * N, v_bytes, bar_v);
+                    ens_bulk_store_cong(ens_cong_store_plan(gv, v_bytes), gv, B);
+                    if (has_next) ens_bulk_load_cong(ens_cong_load_plan(rs.va + head(gv_next), gv_next, v_bytes, rs.v_end), bar_v);
                 }
             } else
 #endif
             {
-                ens_copy_out(a.v + (size_t)grid * N, B, 2 * N, vec16, true, tid, NT);
-                if (has_next) ens_copy_in(A, a.v + (size_t)next * N, 2 * N, vec16, true, tid, NT);
+                ens_copy_cong_out(gv, B, v_bytes, tid, NT);
+                if (has_next) ens_copy_cong_in(rs.va + head(gv_next), gv_next, v_bytes, rs.v_end, tid, NT);
             }
             ens_advect_dye_in_place<R, U>(m, a, B, C_cur, env);
 #ifdef __CUDACC__
@@ -705,7 +837,7 @@ __device__ __forceinline__ void ens_resident_pipelined(const EnsMap<R> &m, const
 #ifdef __CUDACC__
         if (async) {
             if (tid == 0) {
-                ens_bulk_store(a.c + (size_t)grid * N * 3, C_cur, c_bytes);
+                ens_bulk_store_cong(ens_cong_store_plan(gc, c_bytes), gc, C_cur);
                 ens_bulk_wait_read<1>();    // the velocity store (the older group) no longer reads B: the next advect may write it
             }
             if (has_next) {
@@ -714,8 +846,8 @@ __device__ __forceinline__ void ens_resident_pipelined(const EnsMap<R> &m, const
             }
         } else
 #endif
-            ens_copy_out(a.c + (size_t)grid * N * 3, C_cur, 3 * N, vec16, false, tid, NT);
-        uint32_t *tc = C_cur; C_cur = C_oth; C_oth = tc;
+            ens_copy_cong_out(gc, C_cur, c_bytes, tid, NT);
+        unsigned char *tb = rs.ca; rs.ca = rs.cb; rs.cb = tb;      // the next grid's dye is in the other buffer
         env.sync();
     }
 #ifdef __CUDACC__
@@ -729,17 +861,24 @@ __device__ __forceinline__ void ens_reg_body_resident(const EnsArgs &a, unsigned
 {
     EnsMap<R> m;
     ens_map_init(m, a, env.tid, env.nthreads);
-    // 16-byte copies between global and shared memory need N % 4 == 0 (12N and 8N multiples of 16) and aligned arrays
-    const bool vec16 = (m.N & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.v) | reinterpret_cast<uintptr_t>(a.c)) & 15) == 0;
+    const size_t vbuf = ens_reg_vbuf_bytes(m.dim_x, m.dim_y, R), cbuf = ens_reg_cbuf_bytes(m.dim_x, m.dim_y);
+    EnsResident rs;
+    rs.va = smem_raw;
+    rs.vb = smem_raw + vbuf;
+    rs.ca = smem_raw + 2 * vbuf;
+    rs.cb = rs.ca + cbuf;
+    rs.v_end = reinterpret_cast<const unsigned char *>(a.v + (size_t)a.batch * m.N);
+    rs.c_end = reinterpret_cast<const unsigned char *>(a.c + (size_t)a.batch * m.N * 3);
+    rs.cong = ((reinterpret_cast<uintptr_t>(a.v) | reinterpret_cast<uintptr_t>(a.c)) & 15) == 0;
     if constexpr (PIPE) {
         // (a call of many steps amortises the state I/O anyway, and the plain flow's steps are a few % faster)
-        const bool async = Env::kAsync && vec16 && a.n_steps <= a.pipe_max_steps;
-        if (async || Env::kEmulatePipe) {
-            ens_resident_pipelined<R>(m, a, smem_raw, vec16, async, env);
+        const bool async = Env::kAsync && rs.cong && a.n_steps <= a.pipe_max_steps;
+        if (async || (Env::kEmulatePipe && rs.cong)) {
+            ens_resident_pipelined<R>(m, a, rs, rs.cb + cbuf, async, env);
             return;
         }
     }
-    ens_resident_sync<R>(m, a, smem_raw, vec16, env);
+    ens_resident_sync<R>(m, a, rs, env);
 }
 
 // Dye STREAMED through L1/L2 (16 B/node of shared memory: grids too large for 40 B/node): the dye advect gathers it
@@ -771,7 +910,7 @@ __device__ __forceinline__ void ens_reg_body_streamed(const EnsArgs &a, unsigned
             ens_advect_velocity<R, U>(m, a, A, B);
             env.sync();
             ens_drags(m, a, B, step, grid, env);
-            ens_project(m, a, reinterpret_cast<float *>(A), B, env);
+            ens_project(m, a, reinterpret_cast<float *>(A), B, m.even_x, env);
             env.sync();
             ens_advect_dye<R, U>(m, a, B, DyeFetch{C1, m.dim_x}, C2);
             env.sync();                     // (CTA-scope ordering of the dye stores before the next step's reads)

@@ -95,7 +95,7 @@ int  fs_ctx_synchronize(fs_ctx *ctx);
  *              generation with the dye streamed through L1/L2, 5 = first generation, automatic;
  *              6/7/8/9 = register-tiled with 2/4/6/8 rows per thread; 12/14/16/18 = the same, dye streamed;
  *              20/21 = automatic with the bulk-copy pipelined state I/O forced on / off (default: on for calls
- *              of up to 6 steps)
+ *              of up to 3 steps)
  *   "num_sms": (read-only) SMs of the context's device */
 int  fs_ctx_set_option(fs_ctx *ctx, const char *name, int value);
 int  fs_ctx_get_option(fs_ctx *ctx, const char *name, int *value);

@@ -101,3 +101,26 @@ def test_ens_reg_pipelined_flow_on_cpu_threads(emu, port, shape, iters, batch, n
     """The dye-resident R = 2 kernel's PIPELINED flow (in-place dye advect in a grid's last step, next grid's
     state copied in under it) with the bulk copies replaced by cooperative ones at the same program points."""
     run_case(emu, port, shape, iters, batch, n_steps, 2, True, nblocks=nblocks, pipe=1)
+
+
+def test_ens_reg_source_under_address_sanitizer():
+    """The kernel source once more, compiled with -fsanitize=address: the emulator's 'shared memory' is a heap block of
+    exactly the size the launcher allocates and the state arrays are exact-size numpy arrays, so a shared-memory or
+    global access outside them — an off-by-one in the congruent-copy plans, say — is reported.  Runs in a subprocess
+    (the sanitizer runtime has to be preloaded)."""
+    import sys
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not installed")
+    libasan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not libasan or not os.path.isabs(libasan) or not os.path.exists(libasan):
+        pytest.skip("libasan not installed")
+    so = os.path.join(EMU_DIR, "_build", "libens_emu_asan.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+                    "-fsanitize=address", "-I", CUDA_INC, "-o", so, os.path.join(EMU_DIR, "ens_emu.cpp")],
+                   check=True, cwd=EMU_DIR)
+    env = dict(os.environ, LD_PRELOAD=libasan, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "run_cases.py"), so], capture_output=True, text=True,
+                       env=env, timeout=900)
+    assert r.returncode == 0 and "EMU_CASES_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+    assert "AddressSanitizer" not in r.stderr
