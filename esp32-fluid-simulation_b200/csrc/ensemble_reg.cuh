@@ -19,13 +19,18 @@
 //     bit-identical to pois_gs_safe's running sum (sor.cuh: sor_update_coef) — one branch-free path for
 //     interior and wall nodes;
 //   * the mailboxes alias the velocity buffer that is dead during the projection.
-// The two advects keep a node-strided mapping over ALL threads of the CTA, four nodes per thread at a time:
-// the interior case of sample<T> (advect.h:38-42) is evaluated unconditionally on a clamped cell so that
-// the 16 corner loads of four nodes are in flight together, and only nodes whose backtrace left the grid
+// The two advects keep a node-strided mapping over ALL threads of the CTA, two (R = 2) or four nodes per thread
+// at a time: the interior case of sample<T> (advect.h:38-42) is evaluated unconditionally on a clamped cell so
+// that the corner loads of several nodes are in flight together, and only nodes whose backtrace left the grid
 // are redone through the general sample().
+// State I/O (dye resident in shared memory, ens_reg_body_resident): copies between the caller's arrays and shared
+// memory are CONGRUENT modulo 16 bytes for any N (the data pointers of a grid are shifted by its address
+// modulo 16), so they move in 16-byte pieces; calls of few steps pipeline them as bulk copies (cp.async.bulk +
+// mbarriers) under the neighbouring grids' compute — ens_resident_pipelined.
 //
 // The body is a template over an execution environment (thread id, CTA size, barrier) so that
-// tests/emu/ compiles THIS source for the host and runs it on CPU threads against the oracle.
+// tests/emu/ compiles THIS source for the host and runs it on CPU threads against the oracle (also under
+// AddressSanitizer).
 #pragma once
 
 #include "ensemble_common.cuh"
