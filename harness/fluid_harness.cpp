@@ -220,6 +220,9 @@ int run_decomposed(void *gl, State &s, int dim_x, int dim_y, int steps, int iter
 
 int main(int argc, char **argv)
 {
+    // --decomposed N keeps N ranks x 3 streams of mutually waiting kernels on ONE device: each needs a hardware work
+    // queue of its own (include/fluid_b200.h, fs_dist_create); must be set before the CUDA library initialises
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     std::string gpu_lib, cpu_lib, prefix = "ref_", gpu_ops = "all";
     int dim_x = 61, dim_y = 81, steps = 20, iters = 10, n_drags = 4, decomposed = 0;
     for (int i = 1; i < argc; i++) {
