@@ -364,6 +364,10 @@ int fs_dist_create(fs_dist **out, const fs_dist_config *cfg, fs_ctx *ctx)
         if (se == cudaSuccess) se = cudaEventCreateWithFlags(&d->ev_dye, cudaEventDisableTiming);
         if (se == cudaSuccess) se = cudaEventCreateWithFlags(&d->ev_cx, cudaEventDisableTiming);
         if (se != cudaSuccess) {
+            for (int k = 0; k < 6; k++) cudaEventDestroy(d->ev[k]);
+            if (d->xs_v) cudaStreamDestroy(d->xs_v);
+            if (d->xs_c) cudaStreamDestroy(d->xs_c);
+            cudaFree(d->done_side);
             cudaFree(d->arena);
             cudaFree(d->frame);
             delete d;
