@@ -23,11 +23,13 @@ class Violation(AssertionError):
 
 
 class World:
-    def __init__(self, px, py, steps, passes, slow, jitter, seed, skip_wait=None, side_delay=0.0):
+    def __init__(self, px, py, steps, passes, slow, jitter, seed, skip_wait=None, side_delay=0.0, frame=False):
         self.px, self.py, self.n = px, py, px * py
         self.steps, self.passes = steps, passes
         self.slow, self.jitter = slow, jitter
-        self.skip_wait = skip_wait                  # "dye" / "velocity": leave out that event wait (negative test)
+        self.skip_wait = skip_wait                  # "dye" / "velocity" / "frame": leave out that event wait (negative test)
+        self.frame = frame                          # the dye advect also renders the frame: its far corners start from
+                                                    # velocity GHOSTS of the projected velocity
         # extra delay before every side-stream push (a busy copy path): seconds, or {"v": .., "c": ..} per stream
         self.side_delay = side_delay if isinstance(side_delay, dict) else {"v": side_delay, "c": side_delay}
         self.rng = random.Random(seed)
@@ -156,6 +158,10 @@ class Rank:
             self.record(("grad", s))
             if s >= 1 and w.skip_wait != "dye":
                 self.wait_event(("cx", s - 1))
+            if w.frame:
+                if w.skip_wait != "frame":
+                    self.wait_event(("vx", s))                         # (dist.cu: the main stream waits here with a frame)
+                self.read_with_ghosts("v", nxt, s + 1, "frame corners of the dye advect")
             self.read_with_ghosts("c", cur, s, "dye advect")          # 5.
             with w.lock:
                 self.own["c"][nxt] = s + 1
@@ -184,8 +190,8 @@ class Rank:
             self.record(("cx", s))
 
 
-def run_model(px, py, steps=6, passes=3, slow=None, jitter=0.0, seed=1, skip_wait=None, side_delay=0.0):
-    w = World(px, py, steps, passes, slow or {}, jitter, seed, skip_wait, side_delay)
+def run_model(px, py, steps=6, passes=3, slow=None, jitter=0.0, seed=1, skip_wait=None, side_delay=0.0, frame=False):
+    w = World(px, py, steps, passes, slow or {}, jitter, seed, skip_wait, side_delay, frame)
     threads = []
 
     def guard(fn):
@@ -212,23 +218,24 @@ def run_model(px, py, steps=6, passes=3, slow=None, jitter=0.0, seed=1, skip_wai
 
 
 @pytest.mark.parametrize("schedule", ["even", "rank0-slow", "last-slow", "alternate-slow", "jitter", "slow-side-streams"])
+@pytest.mark.parametrize("frame", [False, True], ids=["", "frame"])
 @pytest.mark.parametrize("px,py,passes", [(1, 2, 3), (2, 2, 1), (2, 4, 4)])
-def test_side_stream_exchanges_are_schedule_independent(px, py, passes, schedule):
+def test_side_stream_exchanges_are_schedule_independent(px, py, passes, schedule, frame):
     n = px * py
     slow = {"even": {}, "rank0-slow": {0: 0.004}, "last-slow": {n - 1: 0.004},
             "alternate-slow": {r: 0.003 for r in range(0, n, 2)}, "jitter": {}, "slow-side-streams": {}}[schedule]
     w = run_model(px, py, steps=6, passes=passes, slow=slow, jitter=0.003 if schedule == "jitter" else 0.0, seed=n,
-                  side_delay=0.01 if schedule == "slow-side-streams" else 0.0)
+                  side_delay=0.01 if schedule == "slow-side-streams" else 0.0, frame=frame)
     assert not w.errors, w.errors[:3]
     for rk in w.ranks:                               # every rank got through all steps
         assert rk.own["v"][6 % 2] == 6 and rk.own["c"][6 % 2] == 6
 
 
-@pytest.mark.parametrize("skip", ["dye", "velocity"])
+@pytest.mark.parametrize("skip", ["dye", "velocity", "frame"])
 def test_model_catches_a_missing_event_wait(skip):
     """Without the main stream's wait for the previous step's exchange, a slow neighbour's ghosts are read stale."""
-    late = {"v": 0.03 if skip == "velocity" else 0.0, "c": 0.03 if skip == "dye" else 0.0}   # that stream's pushes arrive late
-    w = run_model(2, 2, steps=4, passes=2, side_delay=late, skip_wait=skip)
+    late = {"v": 0.03 if skip in ("velocity", "frame") else 0.0, "c": 0.03 if skip == "dye" else 0.0}   # those pushes arrive late
+    w = run_model(2, 2, steps=4, passes=2, side_delay=late, skip_wait=skip, frame=skip == "frame")
     assert w.errors and "reads" in w.errors[0], w.errors[:2]
-    w = run_model(2, 2, steps=4, passes=2, side_delay=late)                        # with the waits: late, but correct
+    w = run_model(2, 2, steps=4, passes=2, side_delay=late, frame=skip == "frame")  # with the waits: late, but correct
     assert not w.errors, w.errors[:2]
