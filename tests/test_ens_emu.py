@@ -124,3 +124,11 @@ def test_ens_reg_source_under_address_sanitizer():
                        env=env, timeout=900)
     assert r.returncode == 0 and "EMU_CASES_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
     assert "AddressSanitizer" not in r.stderr
+
+
+def test_ens_reg_source_random_configurations(emu):
+    """A short run of the randomised soak (tests/emu/fuzz.py; the long runs are done by hand)."""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "fuzz.py"), EMU_SO, "7", "12"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "FUZZ_OK" in r.stdout, (r.stdout[-1000:], r.stderr[-3000:])
